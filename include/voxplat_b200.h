@@ -1,0 +1,193 @@
+/*
+ * voxplat_b200.h -- C ABI of the B200-native chunk-rebuild path.
+ *
+ * This is the drop-in boundary for ONE path of the Voxplat engine (reference: kosshi-net/voxplat):
+ * RLE decode/encode -> exposed-voxel cull (with cross-chunk halos) -> 5-level LOD reduction -> splat-list
+ * and near-field quad-mesh buffers.  Every entry point below names the reference interface it replaces
+ * (file:line in the reference tree).  Plain pointers and sizes only; no CUDA, torch or C++ types.
+ *
+ * All byte formats are the reference's:
+ *   voxels   uint8, chunk-local index (z<<2b | y<<b | x), b = root_bitw          chunkset.h:171-188
+ *   chunk id (cz<<by | cy)<<bx | cx over the chunk grid                          chunkset.c:124-126
+ *   RLE      uint32 LE words: run (24 bit) | value<<24, terminated by a 0 word   rle.c:17-26
+ *   splats   int16 x,y,z,colour|shadow<<6 ; per chunk [L0|L1|L2|L3|L4]           mesher.c:497-536, chunkset.c:380-458
+ *   mesh     int16 x,y,z,data per vertex (4 per quad), uint32 indices (6 per quad) mesher.c:321-349
+ *   shadow   uint16 height map, (X+Y) entries per z row                          shadow.h:26-51
+ *
+ * Threading: a vp_ctx may be used from any ONE host thread at a time (the reference's mesher thread,
+ * game.c:77-89); it owns its device buffers, streams and pinned staging.  No GL context is needed.
+ * Errors: every function returns 0 on success or a negative vp_status; vp_last_error() gives text.
+ * There is NO CPU fallback: without a CUDA device vp_ctx_create fails with VP_ERR_NO_DEVICE.
+ */
+#ifndef VOXPLAT_B200_H
+#define VOXPLAT_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define VP_API __attribute__((visibility("default")))
+#else
+#define VP_API
+#endif
+
+#define VP_MAX_LOD_LEVEL 5              /* chunkset.h:11 MAX_LOD_LEVEL */
+
+typedef enum {
+	VP_OK             =  0,
+	VP_ERR_ARG        = -1,             /* bad argument / unsupported geometry */
+	VP_ERR_NO_DEVICE  = -2,             /* no CUDA device: the product never falls back to the CPU */
+	VP_ERR_CUDA       = -3,             /* a CUDA runtime call failed */
+	VP_ERR_ARENA_FULL = -4,             /* output arena too small; counts are valid, grow and retry */
+	VP_ERR_RLE        = -5,             /* malformed RLE stream (length != chunk volume) */
+	VP_ERR_NOT_RESIDENT = -6            /* chunk id outside this context's slab */
+} vp_status;
+
+/* Rebuild flags: which of the dispatcher's two branches to run (chunkset.c:337 `if (c->make_mesh)`). */
+#define VP_REBUILD_SPLAT 1u             /* chunk_make_mask + 5x chunk_make_splatlist + 4x chunk_mask_downsample */
+#define VP_REBUILD_MESH  2u             /* chunk_make_mesh */
+
+typedef struct vp_ctx vp_ctx;
+
+/* World geometry = the fields of struct ChunkSet the path reads (chunkset.h:29-54) plus the slab of
+ * chunk rows this context owns when the world is sharded over several GPUs (z is the slowest chunk
+ * index, so a slab is a contiguous chunk-id range). */
+typedef struct {
+	int32_t  device;                /* CUDA device ordinal */
+	int32_t  root_bitw;             /* ChunkSet.root_bitw: 4..7 (chunk edge 16..128) */
+	int32_t  max_bitw[3];           /* ChunkSet.max_bitw: chunk grid of the WHOLE world */
+	int32_t  slab_z0, slab_z1;      /* owned chunk rows [z0,z1); 0,0 = whole world */
+	uint64_t splat_arena_bytes;     /* device arena for splat lists; 0 = auto */
+	uint64_t mesh_arena_bytes;      /* device arena for VBO+IBO; 0 = auto */
+	uint64_t rle_arena_bytes;       /* device arena for RLE streams in/out; 0 = auto */
+} vp_config;
+
+/* Per-chunk result of one rebuild = what chunkset_manage publishes into struct ChunkMD
+ * (chunkset.c:347-366 mesh branch, :463-501 splat branch).  Offsets are bytes into the arena the
+ * call wrote (host staging for vp_rebuild_batch, device arena for vp_rebuild_device). */
+typedef struct {
+	uint64_t svl_offset;                      /* ChunkMD.svl                       */
+	uint32_t svl_items[VP_MAX_LOD_LEVEL];     /* ChunkMD.svl_items[5] (int16 units) */
+	uint32_t svl_items_total;                 /* ChunkMD.svl_items_total           */
+	uint64_t vbo_offset;                      /* ChunkMD.mesh_vbo                  */
+	uint64_t ibo_offset;                      /* ChunkMD.mesh_ibo                  */
+	uint32_t vbo_items;                       /* ChunkMD.mesh_vbo_items (int16 units)  */
+	uint32_t ibo_items;                       /* ChunkMD.mesh_ibo_items (uint32 units) */
+} vp_chunk_result;
+
+/* ---- context ------------------------------------------------------------------------------- */
+
+/* Replaces chunkset_create + chunkset_clear + shadow_init (chunkset.c:31-121, shadow.h:26-43) for the
+ * device-resident copy of the world: all chunks start as the null (all-air) chunk, the shadow map is
+ * zero-filled and padded (SURVEY 8a' u2/u3). */
+VP_API int  vp_ctx_create(const vp_config *cfg, vp_ctx **out);
+VP_API void vp_ctx_destroy(vp_ctx *ctx);
+VP_API const char *vp_last_error(const vp_ctx *ctx);          /* ctx may be NULL for creation errors */
+VP_API const char *vp_version(void);
+
+/* Re-allocate the output arenas (0 = keep).  Use after VP_ERR_ARENA_FULL: the byte counts reported by
+ * vp_rebuild_device_results are the sizes the batch needs. */
+VP_API int  vp_ctx_resize_arenas(vp_ctx *ctx, uint64_t splat_bytes, uint64_t mesh_bytes);
+
+/* Run all work of this context on an externally owned CUDA stream (a cudaStream_t passed as void*),
+ * e.g. the caller's torch stream, so that the caller's events bracket the kernels.  NULL restores the
+ * context's own stream. */
+VP_API int  vp_ctx_set_stream(vp_ctx *ctx, void *cuda_stream);
+VP_API int  vp_ctx_synchronize(vp_ctx *ctx);
+/* Counters for the bench: kernels launched by this library since the last reset. */
+VP_API uint64_t vp_kernel_launches(vp_ctx *ctx, int reset);
+
+/* ---- world residency (host -> device) -------------------------------------------------------- */
+
+/* Dense upload of n chunks, host_dense = n * R^3 bytes.  Replaces chunk_open_rw + write + chunk_close_rw
+ * (chunkset.c:167-204) for the device copy.  A chunk whose bytes are all zero becomes the null chunk,
+ * like chunk_compress's all-air test (chunkset.c:225-228). */
+VP_API int  vp_upload_chunks_dense(vp_ctx *ctx, const uint32_t *chunk_ids, uint32_t n, const uint8_t *host_dense);
+
+/* RLE upload + device decode: rle_decompress (rle.c:90-116) for n chunks at once.  words = the n streams
+ * back to back (each with its 0 terminator); word_offsets[n+1] = start of each stream in `words`.
+ * A stream equal to the all-air stream {R^3, 0} makes the chunk null (chunkset.c:144-145). */
+VP_API int  vp_upload_chunks_rle(vp_ctx *ctx, const uint32_t *chunk_ids, uint32_t n,
+                          const uint32_t *words, const uint64_t *word_offsets);
+
+/* Make chunks the null chunk (chunkset_clear, chunkset.c:116-117). */
+VP_API int  vp_set_chunks_null(vp_ctx *ctx, const uint32_t *chunk_ids, uint32_t n);
+
+/* Read chunks back as dense bytes (n * R^3); null chunks read as zeros. */
+VP_API int  vp_download_chunks_dense(vp_ctx *ctx, const uint32_t *chunk_ids, uint32_t n, uint8_t *host_dense);
+
+/* rle_compress (rle.c:44-87) of n resident chunks on the device.  On return word_offsets[n+1] holds the
+ * start of every stream inside `words`; total words = word_offsets[n].  VP_ERR_ARENA_FULL if cap_words
+ * is too small (word_offsets is still filled so the caller can size the buffer). */
+VP_API int  vp_encode_chunks_rle(vp_ctx *ctx, const uint32_t *chunk_ids, uint32_t n,
+                          uint32_t *words, uint64_t cap_words, uint64_t *word_offsets);
+
+/* Shadow map rows [z0,z1) in world voxel rows, (X+Y) uint16 each (shadow.h:26-51).  Rows outside the
+ * context's slab (+17 rows of reach) are ignored. */
+VP_API int  vp_upload_shadow_rows(vp_ctx *ctx, uint32_t z0, uint32_t z1, const uint16_t *rows);
+
+/* ---- flat RLE codec: drop-in bodies for rle_compress / rle_decompress (rle.h:7-8) ------------- */
+
+/* Encode `length` bytes; writes at most cap_words words (incl. terminator); *n_words = words needed. */
+VP_API int  vp_rle_compress(vp_ctx *ctx, const uint8_t *data, uint32_t length,
+                     uint32_t *out_words, uint32_t cap_words, uint32_t *n_words);
+/* Decode a 0-terminated stream of n_words words (incl. terminator); *n_bytes = bytes produced. */
+VP_API int  vp_rle_decompress(vp_ctx *ctx, const uint32_t *words, uint32_t n_words,
+                       uint8_t *out, uint32_t cap_bytes, uint32_t *n_bytes);
+
+/* ---- rebuild: the loop body of chunkset_manage (chunkset.c:318-505) for a batch of chunks ------- */
+
+/* Synchronous host-facing call.  For each chunk: VP_REBUILD_SPLAT fills svl_* (five LOD segments,
+ * byte-identical to chunk_make_mask/downsample/splatlist), VP_REBUILD_MESH fills vbo_/ibo_*
+ * (byte-identical to chunk_make_mesh).  `flags` applies to all chunks; if per_chunk_flags != NULL it
+ * overrides per chunk (the reference picks by ChunkMD.make_mesh).  Output bytes are in pinned host
+ * staging owned by ctx, valid until the next rebuild call: *splat_base + svl_offset, *mesh_base +
+ * vbo_offset / ibo_offset. */
+VP_API int  vp_rebuild_batch(vp_ctx *ctx, const uint32_t *chunk_ids, uint32_t n, uint32_t flags,
+                      const uint8_t *per_chunk_flags, vp_chunk_result *results,
+                      const void **splat_base, const void **mesh_base);
+
+/* Asynchronous device-resident variant (what the bench times as `value`): chunk ids are taken from
+ * the host array once (vp_batch_prepare), kernels are enqueued on the context stream, outputs stay
+ * in the device arenas.  vp_rebuild_device_results copies the per-chunk records back. */
+VP_API int  vp_batch_prepare(vp_ctx *ctx, const uint32_t *chunk_ids, uint32_t n, const uint8_t *per_chunk_flags,
+                      uint32_t flags);
+VP_API int  vp_rebuild_device(vp_ctx *ctx);
+VP_API int  vp_rebuild_device_results(vp_ctx *ctx, vp_chunk_result *results, uint64_t *splat_bytes, uint64_t *mesh_bytes);
+/* Device pointers of the arenas (for zero-copy consumers / tests). */
+VP_API void *vp_splat_arena_device(vp_ctx *ctx);
+VP_API void *vp_mesh_arena_device(vp_ctx *ctx);
+/* Copy [0,bytes) of an arena to host memory (which: 0 splat, 1 mesh). */
+VP_API int  vp_arena_download(vp_ctx *ctx, int which, void *host_dst, uint64_t bytes);
+
+/* ---- single-chunk wrappers with the reference's own signatures' meaning (mesher.h:7-37) -------- */
+
+/* chunk_make_mask + chunk_make_splatlist(level 0..4) for one chunk: geometry receives the five
+ * segments, items[5] the int16 counts.  Returns total int16 items or a negative vp_status. */
+VP_API int64_t vp_chunk_make_splatlists(vp_ctx *ctx, uint32_t chunk_id, int16_t *geometry, uint64_t cap_items,
+                                 uint32_t items[VP_MAX_LOD_LEVEL]);
+/* chunk_make_mesh for one chunk. */
+VP_API int  vp_chunk_make_mesh(vp_ctx *ctx, uint32_t chunk_id, int16_t *geometry, uint64_t cap_geometry_items,
+                        uint32_t *geometry_items, uint32_t *index, uint64_t cap_index_items, uint32_t *index_items);
+
+/* ---- multi-GPU slab borders (new: the reference is single-process) ----------------------------- */
+
+/* A border plane = for every chunk column (cx,cy) of one chunk row, one R*R-byte z-slice, packed
+ * (cy*nx + cx)*R*R, nx*ny*R*R bytes in total.  which: 0 = z-slice 0 of the context's FIRST owned chunk
+ * row (send to the rank below: its +z halo), 1 = z-slice R-1 of the LAST owned row (send to the rank
+ * above: its -z halo, needed by mesh AO only).  `device_buf` is a device pointer (e.g. a torch tensor's
+ * data_ptr) that NCCL sends/receives; pack/unpack run on the context stream. */
+VP_API uint64_t vp_halo_plane_bytes(vp_ctx *ctx);
+VP_API int  vp_halo_pack(vp_ctx *ctx, int which, void *device_buf);
+/* which: 0 = plane received from the rank ABOVE (becomes z-slice 0 of ghost row slab_z1),
+ *        1 = plane received from the rank BELOW (becomes z-slice R-1 of ghost row slab_z0-1). */
+VP_API int  vp_halo_unpack(vp_ctx *ctx, int which, const void *device_buf);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VOXPLAT_B200_H */

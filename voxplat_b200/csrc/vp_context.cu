@@ -1,0 +1,714 @@
+// vp_context.cu -- host side of the C ABI (include/voxplat_b200.h): context, resident world,
+// uploads, batch rebuild orchestration, staging.  No CPU compute path exists here: every data
+// transformation is a CUDA kernel (vp_splat.cu, vp_mesh.cu, vp_rle.cu, the small kernels below).
+#include "vp_internal.h"
+#include <cstring>
+#include <cstdio>
+#include <algorithm>
+#include <new>
+
+static thread_local std::string g_create_err;
+
+int vp_fail(vp_ctx *c, int code, const char *what, cudaError_t e)
+{
+	char buf[512];
+	if (e != cudaSuccess) snprintf(buf, sizeof buf, "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
+	else snprintf(buf, sizeof buf, "%s", what);
+	if (c) c->err = buf; else g_create_err = buf;
+	return code;
+}
+
+extern "C" const char *vp_last_error(const vp_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+extern "C" const char *vp_version(void) { return "voxplat_b200 0.1 (sm_100a)"; }
+
+VpWorldDev vp_world_dev(const vp_ctx *c)
+{
+	VpWorldDev w;
+	w.rb = c->rb;
+	for (int i = 0; i < 3; i++) w.bits[i] = c->cfg.max_bitw[i];
+	w.ez0 = c->ez0; w.ez1 = c->ez1;
+	w.slot = c->d_slot;
+	w.vox_pool = c->vox_pool; w.xlo_pool = c->xlo_pool; w.xhi_pool = c->xhi_pool;
+	w.shadow = c->d_shadow; w.sh_z0 = c->sh_z0;
+	w.sh_w = (uint32_t)((c->nx + c->ny) << c->rb);
+	return w;
+}
+
+// ------------------------------------------------------------------------------------------------
+// small kernels
+// ------------------------------------------------------------------------------------------------
+
+// Copies of the x = 0 and x = R-1 planes of freshly written chunks (the contiguous +x / -x halo sources).
+// One CTA per chunk, one thread per (z,y) row: two byte loads at stride R, two coalesced byte stores.
+__global__ void k_extract_xfaces(int rb, const uint8_t *__restrict__ vox_pool, uint8_t *__restrict__ xlo_pool,
+                                 uint8_t *__restrict__ xhi_pool, const int32_t *__restrict__ slots)
+{
+	const int R = 1 << rb, RR = R * R;
+	const int slot = slots[blockIdx.x];
+	if (slot < 0) return;
+	const uint8_t *v = vox_pool + ((size_t)slot << (3 * rb));
+	uint8_t *lo = xlo_pool + (size_t)slot * RR, *hi = xhi_pool + (size_t)slot * RR;
+	for (int r = threadIdx.x; r < RR; r += blockDim.x) {
+		lo[r] = v[(size_t)r << rb];
+		hi[r] = v[((size_t)r << rb) + R - 1];
+	}
+}
+
+cudaError_t vp_launch_extract_xfaces(int rb, const uint8_t *vox_pool, uint8_t *xlo_pool, uint8_t *xhi_pool,
+                                     const int32_t *d_slots, uint32_t n, cudaStream_t s)
+{
+	if (!n) return cudaSuccess;
+	k_extract_xfaces<<<n, 256, 0, s>>>(rb, vox_pool, xlo_pool, xhi_pool, d_slots);
+	return cudaGetLastError();
+}
+
+// Border plane pack / unpack: one R*R slice per chunk column of a chunk row <-> contiguous plane.
+__global__ void k_plane_copy(int rb, uint8_t *__restrict__ vox_pool, const int32_t *__restrict__ row_slots,
+                             uint8_t *__restrict__ plane, int zslice, int unpack)
+{
+	const int R = 1 << rb, RR = R * R;
+	const int slot = row_slots[blockIdx.x];
+	uint4 *pl = reinterpret_cast<uint4 *>(plane + (size_t)blockIdx.x * RR);
+	if (slot < 0) {
+		if (!unpack) for (int i = threadIdx.x; i < RR / 16; i += blockDim.x) pl[i] = make_uint4(0, 0, 0, 0);
+		return;
+	}
+	uint4 *sl = reinterpret_cast<uint4 *>(vox_pool + ((size_t)slot << (3 * rb)) + (size_t)zslice * RR);
+	for (int i = threadIdx.x; i < RR / 16; i += blockDim.x) { if (unpack) sl[i] = pl[i]; else pl[i] = sl[i]; }
+}
+
+// any-nonzero test per chunk column of a received plane (decides which ghost chunks need a slot)
+__global__ void k_plane_nonzero(int rb, const uint8_t *__restrict__ plane, uint32_t *__restrict__ flags)
+{
+	const int RR = 1 << (2 * rb);
+	const uint4 *pl = reinterpret_cast<const uint4 *>(plane + (size_t)blockIdx.x * RR);
+	uint32_t any = 0;
+	for (int i = threadIdx.x; i < RR / 16; i += blockDim.x) { uint4 v = pl[i]; any |= v.x | v.y | v.z | v.w; }
+	any = __syncthreads_or(any != 0);
+	if (threadIdx.x == 0) flags[blockIdx.x] = any;
+}
+
+// ------------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------------
+
+static void ctx_free(vp_ctx *c)
+{
+	if (!c) return;
+	cudaSetDevice(c->cfg.device);
+	cudaFree(c->vox_pool); cudaFree(c->xlo_pool); cudaFree(c->xhi_pool); cudaFree(c->d_slot); cudaFree(c->d_shadow);
+	cudaFree(c->d_ids); cudaFree(c->d_flags); cudaFree(c->d_splat_ids); cudaFree(c->d_mesh_ids); cudaFree(c->d_results);
+	cudaFree(c->d_splat_pos); cudaFree(c->d_mesh_pos);
+	cudaFree(c->d_splat_arena); cudaFree(c->d_mesh_arena); cudaFree(c->d_rle_arena); cudaFree(c->d_arena_state);
+	cudaFree(c->d_tmp_slots); cudaFree(c->d_io);
+	cudaFreeHost(c->h_results); cudaFreeHost(c->h_arena_state); cudaFreeHost(c->h_splat_stage); cudaFreeHost(c->h_mesh_stage);
+	cudaFreeHost(c->h_io_stage);
+	if (c->own_stream) cudaStreamDestroy(c->own_stream);
+	if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+	if (c->ev_a) cudaEventDestroy(c->ev_a);
+	if (c->ev_b) cudaEventDestroy(c->ev_b);
+	delete c;
+}
+
+extern "C" int vp_ctx_create(const vp_config *cfg, vp_ctx **out)
+{
+	if (!cfg || !out) return vp_fail(nullptr, VP_ERR_ARG, "vp_ctx_create: null argument");
+	*out = nullptr;
+	int ndev = 0;
+	cudaError_t e = cudaGetDeviceCount(&ndev);
+	if (e != cudaSuccess || ndev == 0)
+		return vp_fail(nullptr, VP_ERR_NO_DEVICE, "vp_ctx_create: no CUDA device (this library has no CPU path)", e);
+	if (cfg->device < 0 || cfg->device >= ndev) return vp_fail(nullptr, VP_ERR_ARG, "vp_ctx_create: bad device ordinal");
+	if (cfg->root_bitw < 4 || cfg->root_bitw > 7) return vp_fail(nullptr, VP_ERR_ARG, "vp_ctx_create: root_bitw must be 4..7 (chunk edge 16..128)");
+	for (int i = 0; i < 3; i++)
+		if (cfg->max_bitw[i] < 0 || cfg->max_bitw[i] + cfg->root_bitw > 15)
+			return vp_fail(nullptr, VP_ERR_ARG, "vp_ctx_create: world dimension must be <= 32768 voxels");
+	vp_ctx *c = new (std::nothrow) vp_ctx();
+	if (!c) return vp_fail(nullptr, VP_ERR_ARG, "out of host memory");
+	c->cfg = *cfg;
+	c->rb = cfg->root_bitw; c->R = 1 << c->rb;
+	c->nx = 1 << cfg->max_bitw[0]; c->ny = 1 << cfg->max_bitw[1]; c->nz = 1 << cfg->max_bitw[2];
+	if (c->cfg.slab_z1 <= c->cfg.slab_z0) { c->cfg.slab_z0 = 0; c->cfg.slab_z1 = c->nz; }
+	if (c->cfg.slab_z0 < 0 || c->cfg.slab_z1 > c->nz) { delete c; return vp_fail(nullptr, VP_ERR_ARG, "vp_ctx_create: slab outside the world"); }
+	c->ez0 = std::max(0, c->cfg.slab_z0 - 1);
+	c->ez1 = std::min(c->nz, c->cfg.slab_z1 + 1);
+	c->n_ext = (uint32_t)(c->ez1 - c->ez0) * c->nx * c->ny;
+	c->n_slots = c->n_ext;
+	const size_t N = (size_t)1 << (3 * c->rb), RR = (size_t)1 << (2 * c->rb);
+	const size_t owned_vox = (size_t)(c->cfg.slab_z1 - c->cfg.slab_z0) * c->nx * c->ny * N;
+	if (!c->cfg.splat_arena_bytes) c->cfg.splat_arena_bytes = std::max<size_t>(owned_vox * 2, 16u << 20);
+	if (!c->cfg.mesh_arena_bytes) c->cfg.mesh_arena_bytes = std::max<size_t>(owned_vox, 16u << 20);
+	if (!c->cfg.rle_arena_bytes) c->cfg.rle_arena_bytes = std::max<size_t>(owned_vox / 2, 16u << 20);
+
+#define CK(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { int rc = vp_fail(nullptr, VP_ERR_CUDA, #call, e__); ctx_free(c); return rc; } } while (0)
+	CK(cudaSetDevice(cfg->device));
+	CK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+	CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+	CK(cudaEventCreateWithFlags(&c->ev_a, cudaEventDisableTiming));
+	CK(cudaEventCreateWithFlags(&c->ev_b, cudaEventDisableTiming));
+	c->stream = c->own_stream;
+	CK(cudaMalloc(&c->vox_pool, (size_t)c->n_slots * N));
+	CK(cudaMalloc(&c->xlo_pool, (size_t)c->n_slots * RR));
+	CK(cudaMalloc(&c->xhi_pool, (size_t)c->n_slots * RR));
+	CK(cudaMalloc(&c->d_slot, (size_t)c->n_ext * sizeof(int32_t)));
+	CK(cudaMalloc(&c->d_tmp_slots, (size_t)c->n_ext * sizeof(int32_t)));
+	c->h_slot.assign(c->n_ext, -1);
+	c->free_slots.resize(c->n_slots);
+	for (uint32_t i = 0; i < c->n_slots; i++) c->free_slots[i] = c->n_slots - 1 - i;      // pop_back hands out 0,1,2,...
+	CK(cudaMemsetAsync(c->d_slot, 0xFF, (size_t)c->n_ext * sizeof(int32_t), c->stream));
+	// shadow rows: owned voxel rows + 17 rows of reach (LOD-4 samples at z+16, mesh diamond at z+1), plus the
+	// out-of-bounds slack of SURVEY 8a' u3
+	const uint32_t shw = (uint32_t)((c->nx + c->ny) << c->rb), Zw = (uint32_t)c->nz << c->rb;
+	c->sh_z0 = (uint32_t)c->cfg.slab_z0 << c->rb;
+	c->sh_z1 = std::min<uint32_t>(Zw, ((uint32_t)c->cfg.slab_z1 << c->rb) + 17);
+	c->shadow_entries = (size_t)(c->sh_z1 - c->sh_z0) * shw + (size_t)17 * shw + 64;
+	CK(cudaMalloc(&c->d_shadow, c->shadow_entries * sizeof(uint16_t)));
+	CK(cudaMemsetAsync(c->d_shadow, 0, c->shadow_entries * sizeof(uint16_t), c->stream));
+	CK(cudaMalloc(&c->d_splat_arena, c->cfg.splat_arena_bytes));
+	CK(cudaMalloc(&c->d_mesh_arena, c->cfg.mesh_arena_bytes));
+	CK(cudaMalloc(&c->d_rle_arena, c->cfg.rle_arena_bytes));
+	CK(cudaMalloc(&c->d_arena_state, 3 * sizeof(VpArenaDev)));
+	CK(cudaHostAlloc(&c->h_arena_state, 6 * sizeof(VpArenaDev), cudaHostAllocDefault));     // [0..2] readback, [3..5] reset template
+	CK(cudaStreamSynchronize(c->stream));
+#undef CK
+	*out = c;
+	return VP_OK;
+}
+
+extern "C" void vp_ctx_destroy(vp_ctx *ctx) { if (ctx) { cudaSetDevice(ctx->cfg.device); cudaDeviceSynchronize(); ctx_free(ctx); } }
+
+extern "C" int vp_ctx_set_stream(vp_ctx *c, void *cuda_stream)
+{
+	if (!c) return VP_ERR_ARG;
+	VP_CUDA(c, cudaSetDevice(c->cfg.device));
+	VP_CUDA(c, cudaStreamSynchronize(c->stream));
+	c->stream = cuda_stream ? (cudaStream_t)cuda_stream : c->own_stream;
+	return VP_OK;
+}
+
+extern "C" int vp_ctx_synchronize(vp_ctx *c)
+{
+	if (!c) return VP_ERR_ARG;
+	VP_CUDA(c, cudaSetDevice(c->cfg.device));
+	VP_CUDA(c, cudaStreamSynchronize(c->stream));
+	return VP_OK;
+}
+
+extern "C" uint64_t vp_kernel_launches(vp_ctx *c, int reset)
+{
+	uint64_t v = c->launches;
+	if (reset) c->launches = 0;
+	return v;
+}
+
+// pinned staging that only grows
+static int stage_reserve(vp_ctx *c, uint8_t **buf, size_t *cap, size_t need)
+{
+	if (need <= *cap) return VP_OK;
+	if (*buf) { VP_CUDA(c, cudaStreamSynchronize(c->stream)); VP_CUDA(c, cudaFreeHost(*buf)); *buf = nullptr; *cap = 0; }
+	size_t want = std::max(need, (size_t)1 << 20);
+	VP_CUDA(c, cudaHostAlloc((void **)buf, want, cudaHostAllocDefault));
+	*cap = want;
+	return VP_OK;
+}
+
+// extended-slab index of a world chunk id, or -1 when the row is not held here
+static inline int64_t ext_index(const vp_ctx *c, uint32_t id)
+{
+	const uint32_t per_row = (uint32_t)c->nx * c->ny;
+	const uint32_t cz = id / per_row;
+	if (id >= per_row * (uint32_t)c->nz || (int)cz < c->ez0 || (int)cz >= c->ez1) return -1;
+	return (int64_t)id - (int64_t)c->ez0 * per_row;
+}
+
+static inline bool all_zero(const uint8_t *p, size_t n)
+{
+	const uint64_t *q = reinterpret_cast<const uint64_t *>(p);      // chunk volumes are multiples of 8
+	uint64_t acc = 0;
+	for (size_t i = 0; i < n / 8; i++) { acc |= q[i]; if ((i & 511) == 511 && acc) return false; }
+	return acc == 0;
+}
+
+// assign / release slots for a list of chunks; want[i] != 0 means the chunk needs storage
+static int assign_slots(vp_ctx *c, const uint32_t *ids, uint32_t n, const uint8_t *want, std::vector<int32_t> &slots)
+{
+	slots.resize(n);
+	for (uint32_t i = 0; i < n; i++) {
+		int64_t e = ext_index(c, ids[i]);
+		if (e < 0) return vp_fail(c, VP_ERR_NOT_RESIDENT, "chunk id outside this context's slab");
+		int32_t s = c->h_slot[(size_t)e];
+		if (want[i]) {
+			if (s < 0) {
+				if (c->free_slots.empty()) return vp_fail(c, VP_ERR_ARENA_FULL, "chunk pool exhausted");
+				s = (int32_t)c->free_slots.back(); c->free_slots.pop_back();
+				c->h_slot[(size_t)e] = s;
+			}
+		} else if (s >= 0) {
+			c->free_slots.push_back((uint32_t)s);
+			c->h_slot[(size_t)e] = -1; s = -1;
+		}
+		slots[i] = s;
+	}
+	return VP_OK;
+}
+
+// push the slot-table entries of the listed chunks (coalescing consecutive ids)
+static int push_slot_table(vp_ctx *c, const uint32_t *ids, uint32_t n)
+{
+	uint32_t i = 0;
+	while (i < n) {
+		uint32_t j = i + 1;
+		while (j < n && ids[j] == ids[j - 1] + 1) j++;
+		int64_t e = ext_index(c, ids[i]);
+		VP_CUDA(c, cudaMemcpyAsync(c->d_slot + e, c->h_slot.data() + e, (size_t)(j - i) * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+		i = j;
+	}
+	return VP_OK;
+}
+
+extern "C" int vp_upload_chunks_dense(vp_ctx *c, const uint32_t *ids, uint32_t n, const uint8_t *host)
+{
+	if (!c || (n && (!ids || !host))) return vp_fail(c, VP_ERR_ARG, "vp_upload_chunks_dense: null argument");
+	VP_CUDA(c, cudaSetDevice(c->cfg.device));
+	const size_t N = (size_t)1 << (3 * c->rb);
+	std::vector<uint8_t> want(n);
+	for (uint32_t i = 0; i < n; i++) want[i] = !all_zero(host + (size_t)i * N, N);      // chunkset.c:225-228
+	std::vector<int32_t> slots;
+	int rc = assign_slots(c, ids, n, want.data(), slots);
+	if (rc) return rc;
+	// coalesce runs where both the source chunks and the destination slots are consecutive
+	uint32_t i = 0;
+	while (i < n) {
+		if (slots[i] < 0) { i++; continue; }
+		uint32_t j = i + 1;
+		while (j < n && slots[j] == slots[j - 1] + 1) j++;
+		VP_CUDA(c, cudaMemcpyAsync(c->vox_pool + (size_t)slots[i] * N, host + (size_t)i * N, (size_t)(j - i) * N, cudaMemcpyHostToDevice, c->stream));
+		i = j;
+	}
+	rc = push_slot_table(c, ids, n);
+	if (rc) return rc;
+	VP_CUDA(c, cudaMemcpyAsync(c->d_tmp_slots, slots.data(), (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+	VP_CUDA(c, vp_launch_extract_xfaces(c->rb, c->vox_pool, c->xlo_pool, c->xhi_pool, c->d_tmp_slots, n, c->stream));
+	c->launches++;
+	VP_CUDA(c, cudaStreamSynchronize(c->stream));      // `slots` / caller memory may go away
+	return VP_OK;
+}
+
+extern "C" int vp_set_chunks_null(vp_ctx *c, const uint32_t *ids, uint32_t n)
+{
+	if (!c || (n && !ids)) return vp_fail(c, VP_ERR_ARG, "vp_set_chunks_null: null argument");
+	VP_CUDA(c, cudaSetDevice(c->cfg.device));
+	std::vector<uint8_t> want(n, 0);
+	std::vector<int32_t> slots;
+	int rc = assign_slots(c, ids, n, want.data(), slots);
+	if (rc) return rc;
+	rc = push_slot_table(c, ids, n);
+	if (rc) return rc;
+	VP_CUDA(c, cudaStreamSynchronize(c->stream));
+	return VP_OK;
+}
+
+extern "C" int vp_download_chunks_dense(vp_ctx *c, const uint32_t *ids, uint32_t n, uint8_t *host)
+{
+	if (!c || (n && (!ids || !host))) return vp_fail(c, VP_ERR_ARG, "vp_download_chunks_dense: null argument");
+	VP_CUDA(c, cudaSetDevice(c->cfg.device));
+	const size_t N = (size_t)1 << (3 * c->rb);
+	for (uint32_t i = 0; i < n; i++) {
+		int64_t e = ext_index(c, ids[i]);
+		if (e < 0) return vp_fail(c, VP_ERR_NOT_RESIDENT, "chunk id outside this context's slab");
+		int32_t s = c->h_slot[(size_t)e];
+		if (s < 0) memset(host + (size_t)i * N, 0, N);
+		else VP_CUDA(c, cudaMemcpyAsync(host + (size_t)i * N, c->vox_pool + (size_t)s * N, N, cudaMemcpyDeviceToHost, c->stream));
+	}
+	VP_CUDA(c, cudaStreamSynchronize(c->stream));
+	return VP_OK;
+}
+
+extern "C" int vp_upload_shadow_rows(vp_ctx *c, uint32_t z0, uint32_t z1, const uint16_t *rows)
+{
+	if (!c || !rows || z1 < z0) return vp_fail(c, VP_ERR_ARG, "vp_upload_shadow_rows: bad argument");
+	VP_CUDA(c, cudaSetDevice(c->cfg.device));
+	const uint32_t shw = (uint32_t)((c->nx + c->ny) << c->rb);
+	uint32_t a = std::max(z0, c->sh_z0), b = std::min(z1, c->sh_z1);
+	if (a < b)
+		VP_CUDA(c, cudaMemcpyAsync(c->d_shadow + (size_t)(a - c->sh_z0) * shw, rows + (size_t)(a - z0) * shw,
+		                           (size_t)(b - a) * shw * sizeof(uint16_t), cudaMemcpyHostToDevice, c->stream));
+	VP_CUDA(c, cudaStreamSynchronize(c->stream));
+	return VP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// rebuild
+// ------------------------------------------------------------------------------------------------
+
+static int batch_reserve(vp_ctx *c, uint32_t n)
+{
+	if (n <= c->batch_cap) return VP_OK;
+	VP_CUDA(c, cudaStreamSynchronize(c->stream));
+	cudaFree(c->d_ids); cudaFree(c->d_flags); cudaFree(c->d_splat_ids); cudaFree(c->d_mesh_ids); cudaFree(c->d_results);
+	cudaFree(c->d_splat_pos); cudaFree(c->d_mesh_pos);
+	cudaFreeHost(c->h_results);
+	c->d_ids = c->d_splat_ids = c->d_mesh_ids = c->d_splat_pos = c->d_mesh_pos = nullptr; c->d_flags = nullptr; c->d_results = nullptr; c->h_results = nullptr;
+	c->batch_cap = 0;
+	uint32_t cap = std::max<uint32_t>(n, 1024);
+	VP_CUDA(c, cudaMalloc(&c->d_ids, (size_t)cap * 4));
+	VP_CUDA(c, cudaMalloc(&c->d_flags, (size_t)cap));
+	VP_CUDA(c, cudaMalloc(&c->d_splat_ids, (size_t)cap * 4));
+	VP_CUDA(c, cudaMalloc(&c->d_mesh_ids, (size_t)cap * 4));
+	VP_CUDA(c, cudaMalloc(&c->d_splat_pos, (size_t)cap * 4));
+	VP_CUDA(c, cudaMalloc(&c->d_mesh_pos, (size_t)cap * 4));
+	VP_CUDA(c, cudaMalloc(&c->d_results, (size_t)cap * sizeof(VpResultDev)));
+	VP_CUDA(c, cudaHostAlloc(&c->h_results, (size_t)cap * sizeof(VpResultDev), cudaHostAllocDefault));
+	c->batch_cap = cap;
+	return VP_OK;
+}
+
+extern "C" int vp_batch_prepare(vp_ctx *c, const uint32_t *ids, uint32_t n, const uint8_t *per_chunk_flags, uint32_t flags)
+{
+	if (!c || (n && !ids)) return vp_fail(c, VP_ERR_ARG, "vp_batch_prepare: null argument");
+	VP_CUDA(c, cudaSetDevice(c->cfg.device));
+	int rc = batch_reserve(c, n);
+	if (rc) return rc;
+	std::vector<uint32_t> sid, spos, mid, mpos;
+	for (uint32_t i = 0; i < n; i++) {
+		const uint32_t per_row = (uint32_t)c->nx * c->ny, cz = ids[i] / per_row;
+		if (ids[i] >= per_row * (uint32_t)c->nz || (int)cz < c->cfg.slab_z0 || (int)cz >= c->cfg.slab_z1)
+			return vp_fail(c, VP_ERR_NOT_RESIDENT, "vp_batch_prepare: chunk id outside the owned slab");
+		uint32_t f = per_chunk_flags ? per_chunk_flags[i] : flags;
+		if (f & VP_REBUILD_SPLAT) { sid.push_back(ids[i]); spos.push_back(i); }
+		if (f & VP_REBUILD_MESH) { mid.push_back(ids[i]); mpos.push_back(i); }
+	}
+	c->batch_n = n; c->n_splat = (uint32_t)sid.size(); c->n_mesh = (uint32_t)mid.size();
+	if (c->n_splat) {
+		VP_CUDA(c, cudaMemcpyAsync(c->d_splat_ids, sid.data(), sid.size() * 4, cudaMemcpyHostToDevice, c->stream));
+		VP_CUDA(c, cudaMemcpyAsync(c->d_splat_pos, spos.data(), spos.size() * 4, cudaMemcpyHostToDevice, c->stream));
+	}
+	if (c->n_mesh) {
+		VP_CUDA(c, cudaMemcpyAsync(c->d_mesh_ids, mid.data(), mid.size() * 4, cudaMemcpyHostToDevice, c->stream));
+		VP_CUDA(c, cudaMemcpyAsync(c->d_mesh_pos, mpos.data(), mpos.size() * 4, cudaMemcpyHostToDevice, c->stream));
+	}
+	// reset template for the arena states
+	for (int a = 0; a < 3; a++) { c->h_arena_state[3 + a].cursor = 0; c->h_arena_state[3 + a].overflow = 0; c->h_arena_state[3 + a].pad = 0; }
+	c->h_arena_state[3].capacity = c->cfg.splat_arena_bytes;
+	c->h_arena_state[4].capacity = c->cfg.mesh_arena_bytes;
+	c->h_arena_state[5].capacity = c->cfg.rle_arena_bytes;
+	VP_CUDA(c, cudaStreamSynchronize(c->stream));
+	return VP_OK;
+}
+
+extern "C" int vp_rebuild_device(vp_ctx *c)
+{
+	if (!c) return VP_ERR_ARG;
+	VP_CUDA(c, cudaSetDevice(c->cfg.device));
+	VP_CUDA(c, cudaMemcpyAsync(c->d_arena_state, c->h_arena_state + 3, 2 * sizeof(VpArenaDev), cudaMemcpyHostToDevice, c->stream));
+	VP_CUDA(c, cudaMemsetAsync(c->d_results, 0, (size_t)c->batch_n * sizeof(VpResultDev), c->stream));
+	VpWorldDev w = vp_world_dev(c);
+	if (c->n_splat) {
+		VP_CUDA(c, vp_launch_splat(w, c->d_splat_ids, c->n_splat, c->d_results, c->d_splat_pos, c->d_splat_arena, c->d_arena_state + 0, c->stream));
+		c->launches++;
+	}
+	if (c->n_mesh) {
+		VP_CUDA(c, vp_launch_mesh(w, c->d_mesh_ids, c->n_mesh, c->d_results, c->d_mesh_pos, c->d_mesh_arena, c->d_arena_state + 1, c->stream));
+		c->launches++;
+	}
+	return VP_OK;
+}
+
+extern "C" int vp_rebuild_device_results(vp_ctx *c, vp_chunk_result *results, uint64_t *splat_bytes, uint64_t *mesh_bytes)
+{
+	if (!c) return VP_ERR_ARG;
+	VP_CUDA(c, cudaSetDevice(c->cfg.device));
+	if (c->batch_n) VP_CUDA(c, cudaMemcpyAsync(c->h_results, c->d_results, (size_t)c->batch_n * sizeof(VpResultDev), cudaMemcpyDeviceToHost, c->stream));
+	VP_CUDA(c, cudaMemcpyAsync(c->h_arena_state, c->d_arena_state, 2 * sizeof(VpArenaDev), cudaMemcpyDeviceToHost, c->stream));
+	VP_CUDA(c, cudaStreamSynchronize(c->stream));
+	if (results && c->batch_n) memcpy(results, c->h_results, (size_t)c->batch_n * sizeof(VpResultDev));
+	if (splat_bytes) *splat_bytes = c->h_arena_state[0].cursor;
+	if (mesh_bytes) *mesh_bytes = c->h_arena_state[1].cursor;
+	if (c->h_arena_state[0].overflow || c->h_arena_state[1].overflow)
+		return vp_fail(c, VP_ERR_ARENA_FULL, "output arena too small (cursor values give the required bytes)");
+	return VP_OK;
+}
+
+extern "C" void *vp_splat_arena_device(vp_ctx *c) { return c ? c->d_splat_arena : nullptr; }
+extern "C" void *vp_mesh_arena_device(vp_ctx *c) { return c ? c->d_mesh_arena : nullptr; }
+
+extern "C" int vp_arena_download(vp_ctx *c, int which, void *host_dst, uint64_t bytes)
+{
+	if (!c || !host_dst || which < 0 || which > 1) return vp_fail(c, VP_ERR_ARG, "vp_arena_download: bad argument");
+	VP_CUDA(c, cudaSetDevice(c->cfg.device));
+	VP_CUDA(c, cudaMemcpyAsync(host_dst, which ? c->d_mesh_arena : c->d_splat_arena, bytes, cudaMemcpyDeviceToHost, c->stream));
+	VP_CUDA(c, cudaStreamSynchronize(c->stream));
+	return VP_OK;
+}
+
+extern "C" int vp_ctx_resize_arenas(vp_ctx *c, uint64_t splat_bytes, uint64_t mesh_bytes)
+{
+	if (!c) return VP_ERR_ARG;
+	VP_CUDA(c, cudaSetDevice(c->cfg.device));
+	VP_CUDA(c, cudaStreamSynchronize(c->stream));
+	if (splat_bytes && splat_bytes != c->cfg.splat_arena_bytes) {
+		cudaFree(c->d_splat_arena); c->d_splat_arena = nullptr;
+		VP_CUDA(c, cudaMalloc(&c->d_splat_arena, splat_bytes));
+		c->cfg.splat_arena_bytes = splat_bytes;
+	}
+	if (mesh_bytes && mesh_bytes != c->cfg.mesh_arena_bytes) {
+		cudaFree(c->d_mesh_arena); c->d_mesh_arena = nullptr;
+		VP_CUDA(c, cudaMalloc(&c->d_mesh_arena, mesh_bytes));
+		c->cfg.mesh_arena_bytes = mesh_bytes;
+	}
+	return VP_OK;
+}
+
+extern "C" int vp_rebuild_batch(vp_ctx *c, const uint32_t *ids, uint32_t n, uint32_t flags, const uint8_t *per_chunk_flags,
+                                vp_chunk_result *results, const void **splat_base, const void **mesh_base)
+{
+	int rc = vp_batch_prepare(c, ids, n, per_chunk_flags, flags);
+	if (rc) return rc;
+	rc = vp_rebuild_device(c);
+	if (rc) return rc;
+	uint64_t sb = 0, mb = 0;
+	rc = vp_rebuild_device_results(c, results, &sb, &mb);
+	if (rc) return rc;
+	if ((rc = stage_reserve(c, &c->h_splat_stage, &c->splat_stage_cap, sb))) return rc;
+	if ((rc = stage_reserve(c, &c->h_mesh_stage, &c->mesh_stage_cap, mb))) return rc;
+	if (sb) VP_CUDA(c, cudaMemcpyAsync(c->h_splat_stage, c->d_splat_arena, sb, cudaMemcpyDeviceToHost, c->stream));
+	if (mb) VP_CUDA(c, cudaMemcpyAsync(c->h_mesh_stage, c->d_mesh_arena, mb, cudaMemcpyDeviceToHost, c->stream));
+	VP_CUDA(c, cudaStreamSynchronize(c->stream));
+	if (splat_base) *splat_base = c->h_splat_stage;
+	if (mesh_base) *mesh_base = c->h_mesh_stage;
+	return VP_OK;
+}
+
+// ---- single-chunk wrappers (mesher.h:7-37 semantics) ------------------------------------------------
+
+extern "C" int64_t vp_chunk_make_splatlists(vp_ctx *c, uint32_t chunk_id, int16_t *geometry, uint64_t cap_items, uint32_t items[VP_MAX_LOD_LEVEL])
+{
+	vp_chunk_result r;
+	const void *sb = nullptr;
+	int rc = vp_rebuild_batch(c, &chunk_id, 1, VP_REBUILD_SPLAT, nullptr, &r, &sb, nullptr);
+	if (rc) return rc;
+	for (int l = 0; l < VP_MAX_LOD_LEVEL; l++) items[l] = r.svl_items[l];
+	if (r.svl_items_total > cap_items) return vp_fail(c, VP_ERR_ARENA_FULL, "vp_chunk_make_splatlists: geometry buffer too small");
+	if (r.svl_items_total) memcpy(geometry, (const uint8_t *)sb + r.svl_offset, (size_t)r.svl_items_total * 2);
+	return (int64_t)r.svl_items_total;
+}
+
+extern "C" int vp_chunk_make_mesh(vp_ctx *c, uint32_t chunk_id, int16_t *geometry, uint64_t cap_geometry_items, uint32_t *geometry_items,
+                                  uint32_t *index, uint64_t cap_index_items, uint32_t *index_items)
+{
+	vp_chunk_result r;
+	const void *mb = nullptr;
+	int rc = vp_rebuild_batch(c, &chunk_id, 1, VP_REBUILD_MESH, nullptr, &r, nullptr, &mb);
+	if (rc) return rc;
+	*geometry_items = r.vbo_items; *index_items = r.ibo_items;
+	if (r.vbo_items > cap_geometry_items || r.ibo_items > cap_index_items)
+		return vp_fail(c, VP_ERR_ARENA_FULL, "vp_chunk_make_mesh: output buffer too small");
+	if (r.vbo_items) memcpy(geometry, (const uint8_t *)mb + r.vbo_offset, (size_t)r.vbo_items * 2);
+	if (r.ibo_items) memcpy(index, (const uint8_t *)mb + r.ibo_offset, (size_t)r.ibo_items * 4);
+	return VP_OK;
+}
+
+// ---- multi-GPU slab borders ---------------------------------------------------------------------------
+
+extern "C" uint64_t vp_halo_plane_bytes(vp_ctx *c) { return c ? (uint64_t)c->nx * c->ny << (2 * c->rb) : 0; }
+
+extern "C" int vp_halo_pack(vp_ctx *c, int which, void *device_buf)
+{
+	if (!c || !device_buf || which < 0 || which > 1) return vp_fail(c, VP_ERR_ARG, "vp_halo_pack: bad argument");
+	VP_CUDA(c, cudaSetDevice(c->cfg.device));
+	const uint32_t per_row = (uint32_t)c->nx * c->ny;
+	const int row = which == 0 ? c->cfg.slab_z0 : c->cfg.slab_z1 - 1;
+	const int32_t *row_slots = c->d_slot + (size_t)(row - c->ez0) * per_row;
+	k_plane_copy<<<per_row, 256, 0, c->stream>>>(c->rb, c->vox_pool, row_slots, (uint8_t *)device_buf, which == 0 ? 0 : c->R - 1, 0);
+	VP_CUDA(c, cudaGetLastError());
+	c->launches++;
+	return VP_OK;
+}
+
+extern "C" int vp_halo_unpack(vp_ctx *c, int which, const void *device_buf)
+{
+	if (!c || !device_buf || which < 0 || which > 1) return vp_fail(c, VP_ERR_ARG, "vp_halo_unpack: bad argument");
+	VP_CUDA(c, cudaSetDevice(c->cfg.device));
+	const uint32_t per_row = (uint32_t)c->nx * c->ny;
+	const int row = which == 0 ? c->cfg.slab_z1 : c->cfg.slab_z0 - 1;
+	if (row < c->ez0 || row >= c->ez1) return vp_fail(c, VP_ERR_ARG, "vp_halo_unpack: no ghost row on that side");
+	const size_t N = (size_t)1 << (3 * c->rb);
+	// which ghost chunks have any solid voxel in the plane?
+	uint32_t *d_flags32 = reinterpret_cast<uint32_t *>(c->d_tmp_slots);
+	k_plane_nonzero<<<per_row, 256, 0, c->stream>>>(c->rb, (const uint8_t *)device_buf, d_flags32);
+	VP_CUDA(c, cudaGetLastError());
+	std::vector<uint32_t> flags(per_row);
+	VP_CUDA(c, cudaMemcpyAsync(flags.data(), d_flags32, (size_t)per_row * 4, cudaMemcpyDeviceToHost, c->stream));
+	VP_CUDA(c, cudaStreamSynchronize(c->stream));
+	std::vector<uint32_t> ids(per_row);
+	std::vector<uint8_t> want(per_row);
+	for (uint32_t i = 0; i < per_row; i++) { ids[i] = (uint32_t)row * per_row + i; want[i] = flags[i] != 0; }
+	std::vector<int32_t> slots;
+	int rc = assign_slots(c, ids.data(), per_row, want.data(), slots);
+	if (rc) return rc;
+	for (uint32_t i = 0; i < per_row; i++)      // ghost chunks hold only the border slice; keep the rest deterministic
+		if (slots[i] >= 0) VP_CUDA(c, cudaMemsetAsync(c->vox_pool + (size_t)slots[i] * N, 0, N, c->stream));
+	if ((rc = push_slot_table(c, ids.data(), per_row))) return rc;
+	const int32_t *row_slots = c->d_slot + (size_t)(row - c->ez0) * per_row;
+	k_plane_copy<<<per_row, 256, 0, c->stream>>>(c->rb, c->vox_pool, row_slots, (uint8_t *)const_cast<void *>(device_buf), which == 0 ? 0 : c->R - 1, 1);
+	VP_CUDA(c, cudaGetLastError());
+	VP_CUDA(c, vp_launch_extract_xfaces(c->rb, c->vox_pool, c->xlo_pool, c->xhi_pool, row_slots, per_row, c->stream));
+	c->launches += 3;
+	VP_CUDA(c, cudaStreamSynchronize(c->stream));
+	return VP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// RLE: upload + decode, encode of resident chunks, flat codec
+// ------------------------------------------------------------------------------------------------
+
+static int dio_reserve(vp_ctx *c, size_t need)
+{
+	if (need <= c->d_io_cap) return VP_OK;
+	VP_CUDA(c, cudaStreamSynchronize(c->stream));
+	cudaFree(c->d_io); c->d_io = nullptr; c->d_io_cap = 0;
+	size_t want = std::max(need, (size_t)4 << 20);
+	VP_CUDA(c, cudaMalloc(&c->d_io, want));
+	c->d_io_cap = want;
+	return VP_OK;
+}
+
+extern "C" int vp_upload_chunks_rle(vp_ctx *c, const uint32_t *ids, uint32_t n, const uint32_t *words, const uint64_t *word_offsets)
+{
+	if (!c || (n && (!ids || !words || !word_offsets))) return vp_fail(c, VP_ERR_ARG, "vp_upload_chunks_rle: null argument");
+	if (!n) return VP_OK;
+	VP_CUDA(c, cudaSetDevice(c->cfg.device));
+	const uint32_t N = 1u << (3 * c->rb);
+	const uint64_t total_words = word_offsets[n] - word_offsets[0];
+	if (total_words * 4 > c->cfg.rle_arena_bytes) return vp_fail(c, VP_ERR_ARENA_FULL, "vp_upload_chunks_rle: rle arena too small for this batch");
+	std::vector<uint8_t> want(n);
+	for (uint32_t i = 0; i < n; i++) {
+		if (word_offsets[i + 1] < word_offsets[i] + 2) return vp_fail(c, VP_ERR_RLE, "vp_upload_chunks_rle: stream shorter than 2 words");
+		want[i] = words[word_offsets[i]] != N;             // first word == {run N, value 0}: the null chunk (chunkset.c:225-228)
+	}
+	std::vector<int32_t> slots;
+	int rc = assign_slots(c, ids, n, want.data(), slots);
+	if (rc) return rc;
+	// device copies: words -> rle arena, offsets (relative to the first word) + slots + status -> d_io
+	std::vector<unsigned long long> rel(n + 1);
+	for (uint32_t i = 0; i <= n; i++) rel[i] = word_offsets[i] - word_offsets[0];
+	const size_t off_bytes = (size_t)(n + 1) * 8, slot_bytes = (size_t)n * 4;
+	if ((rc = dio_reserve(c, off_bytes + slot_bytes + 16))) return rc;
+	unsigned long long *d_off = reinterpret_cast<unsigned long long *>(c->d_io);
+	int32_t *d_slots = reinterpret_cast<int32_t *>(c->d_io + off_bytes);
+	uint32_t *d_status = reinterpret_cast<uint32_t *>(c->d_io + off_bytes + ((slot_bytes + 7) & ~(size_t)7));
+	VP_CUDA(c, cudaMemcpyAsync(c->d_rle_arena, words + word_offsets[0], total_words * 4, cudaMemcpyHostToDevice, c->stream));
+	VP_CUDA(c, cudaMemcpyAsync(d_off, rel.data(), off_bytes, cudaMemcpyHostToDevice, c->stream));
+	VP_CUDA(c, cudaMemcpyAsync(d_slots, slots.data(), slot_bytes, cudaMemcpyHostToDevice, c->stream));
+	VP_CUDA(c, cudaMemsetAsync(d_status, 0, 4, c->stream));
+	VP_CUDA(c, vp_launch_rle_decode(reinterpret_cast<const uint32_t *>(c->d_rle_arena), d_off, d_slots, n, c->vox_pool, N, d_status, c->stream));
+	VP_CUDA(c, vp_launch_extract_xfaces(c->rb, c->vox_pool, c->xlo_pool, c->xhi_pool, d_slots, n, c->stream));
+	c->launches += 2;
+	if ((rc = push_slot_table(c, ids, n))) return rc;
+	uint32_t status = 0;
+	VP_CUDA(c, cudaMemcpyAsync(&status, d_status, 4, cudaMemcpyDeviceToHost, c->stream));
+	VP_CUDA(c, cudaStreamSynchronize(c->stream));
+	if (status) return vp_fail(c, VP_ERR_RLE, "vp_upload_chunks_rle: a stream does not expand to exactly one chunk volume");
+	return VP_OK;
+}
+
+extern "C" int vp_encode_chunks_rle(vp_ctx *c, const uint32_t *ids, uint32_t n, uint32_t *words, uint64_t cap_words, uint64_t *word_offsets)
+{
+	if (!c || (n && (!ids || !word_offsets))) return vp_fail(c, VP_ERR_ARG, "vp_encode_chunks_rle: null argument");
+	VP_CUDA(c, cudaSetDevice(c->cfg.device));
+	const uint32_t N = 1u << (3 * c->rb);
+	std::vector<int32_t> slots(n);
+	for (uint32_t i = 0; i < n; i++) {
+		int64_t e = ext_index(c, ids[i]);
+		if (e < 0) return vp_fail(c, VP_ERR_NOT_RESIDENT, "chunk id outside this context's slab");
+		slots[i] = c->h_slot[(size_t)e];
+	}
+	const size_t off_bytes = (size_t)n * 8, cnt_bytes = (size_t)n * 4, slot_bytes = (size_t)n * 4;
+	int rc = dio_reserve(c, off_bytes + cnt_bytes + slot_bytes + 16);
+	if (rc) return rc;
+	unsigned long long *d_off = reinterpret_cast<unsigned long long *>(c->d_io);
+	uint32_t *d_cnt = reinterpret_cast<uint32_t *>(c->d_io + off_bytes);
+	int32_t *d_slots = reinterpret_cast<int32_t *>(c->d_io + off_bytes + cnt_bytes);
+	c->h_arena_state[5].cursor = 0; c->h_arena_state[5].capacity = c->cfg.rle_arena_bytes; c->h_arena_state[5].overflow = 0; c->h_arena_state[5].pad = 0;
+	VP_CUDA(c, cudaMemcpyAsync(c->d_arena_state + 2, c->h_arena_state + 5, sizeof(VpArenaDev), cudaMemcpyHostToDevice, c->stream));
+	VP_CUDA(c, cudaMemcpyAsync(d_slots, slots.data(), slot_bytes, cudaMemcpyHostToDevice, c->stream));
+	VP_CUDA(c, vp_launch_rle_encode(c->vox_pool, d_slots, n, N, reinterpret_cast<uint32_t *>(c->d_rle_arena), c->d_arena_state + 2, d_off, d_cnt, c->stream));
+	c->launches++;
+	std::vector<unsigned long long> off(n);
+	std::vector<uint32_t> cnt(n);
+	VP_CUDA(c, cudaMemcpyAsync(off.data(), d_off, off_bytes, cudaMemcpyDeviceToHost, c->stream));
+	VP_CUDA(c, cudaMemcpyAsync(cnt.data(), d_cnt, cnt_bytes, cudaMemcpyDeviceToHost, c->stream));
+	VP_CUDA(c, cudaMemcpyAsync(c->h_arena_state + 2, c->d_arena_state + 2, sizeof(VpArenaDev), cudaMemcpyDeviceToHost, c->stream));
+	VP_CUDA(c, cudaStreamSynchronize(c->stream));
+	if (c->h_arena_state[2].overflow) return vp_fail(c, VP_ERR_ARENA_FULL, "vp_encode_chunks_rle: rle arena too small");
+	uint64_t acc = 0;
+	for (uint32_t i = 0; i < n; i++) { word_offsets[i] = acc; acc += slots[i] < 0 ? 2 : cnt[i]; }
+	word_offsets[n] = acc;
+	if (acc > cap_words || !words) return vp_fail(c, VP_ERR_ARENA_FULL, "vp_encode_chunks_rle: output buffer too small (word_offsets[n] words needed)");
+	const uint64_t used = c->h_arena_state[2].cursor;
+	if ((rc = stage_reserve(c, &c->h_io_stage, &c->io_stage_cap, used))) return rc;
+	if (used) VP_CUDA(c, cudaMemcpyAsync(c->h_io_stage, c->d_rle_arena, used, cudaMemcpyDeviceToHost, c->stream));
+	VP_CUDA(c, cudaStreamSynchronize(c->stream));
+	for (uint32_t i = 0; i < n; i++) {
+		uint32_t *dst = words + word_offsets[i];
+		if (slots[i] < 0) { dst[0] = N; dst[1] = 0; }                    // the shared null stream (chunkset.c:98,117)
+		else memcpy(dst, c->h_io_stage + off[i] * 4, (size_t)cnt[i] * 4);
+	}
+	return VP_OK;
+}
+
+extern "C" int vp_rle_compress(vp_ctx *c, const uint8_t *data, uint32_t length, uint32_t *out_words, uint32_t cap_words, uint32_t *n_words)
+{
+	if (!c || !data || !n_words) return vp_fail(c, VP_ERR_ARG, "vp_rle_compress: null argument");
+	if (length == 0 || (length & 15) || length > 0xFFFFFFu)
+		return vp_fail(c, VP_ERR_ARG, "vp_rle_compress: length must be a multiple of 16 and <= 0xFFFFFF (chunk volumes up to 128^3)");
+	VP_CUDA(c, cudaSetDevice(c->cfg.device));
+	if ((size_t)(length + 1) * 4 > c->cfg.rle_arena_bytes) return vp_fail(c, VP_ERR_ARENA_FULL, "vp_rle_compress: rle arena too small");
+	int rc = dio_reserve(c, (size_t)length + 64);
+	if (rc) return rc;
+	unsigned long long *d_off = reinterpret_cast<unsigned long long *>(c->d_io);
+	uint32_t *d_cnt = reinterpret_cast<uint32_t *>(c->d_io + 8);
+	uint8_t *d_src = c->d_io + 64;
+	c->h_arena_state[5].cursor = 0; c->h_arena_state[5].capacity = c->cfg.rle_arena_bytes; c->h_arena_state[5].overflow = 0; c->h_arena_state[5].pad = 0;
+	VP_CUDA(c, cudaMemcpyAsync(c->d_arena_state + 2, c->h_arena_state + 5, sizeof(VpArenaDev), cudaMemcpyHostToDevice, c->stream));
+	VP_CUDA(c, cudaMemcpyAsync(d_src, data, length, cudaMemcpyHostToDevice, c->stream));
+	VP_CUDA(c, vp_launch_rle_encode(d_src, nullptr, 1, length, reinterpret_cast<uint32_t *>(c->d_rle_arena), c->d_arena_state + 2, d_off, d_cnt, c->stream));
+	c->launches++;
+	uint32_t cnt = 0;
+	VP_CUDA(c, cudaMemcpyAsync(&cnt, d_cnt, 4, cudaMemcpyDeviceToHost, c->stream));
+	VP_CUDA(c, cudaStreamSynchronize(c->stream));
+	*n_words = cnt;
+	if (cnt > cap_words || !out_words) return vp_fail(c, VP_ERR_ARENA_FULL, "vp_rle_compress: output buffer too small");
+	VP_CUDA(c, cudaMemcpyAsync(out_words, c->d_rle_arena, (size_t)cnt * 4, cudaMemcpyDeviceToHost, c->stream));
+	VP_CUDA(c, cudaStreamSynchronize(c->stream));
+	return VP_OK;
+}
+
+extern "C" int vp_rle_decompress(vp_ctx *c, const uint32_t *words, uint32_t n_words, uint8_t *out, uint32_t cap_bytes, uint32_t *n_bytes)
+{
+	if (!c || !words || !out || !n_bytes || n_words < 2) return vp_fail(c, VP_ERR_ARG, "vp_rle_decompress: bad argument");
+	VP_CUDA(c, cudaSetDevice(c->cfg.device));
+	uint64_t total = 0;
+	for (uint32_t i = 0; i + 1 < n_words; i++) total += words[i] & 0xFFFFFFu;        // output size (metadata only)
+	*n_bytes = (uint32_t)std::min<uint64_t>(total, 0xFFFFFFFFu);
+	if (total > cap_bytes) return vp_fail(c, VP_ERR_ARENA_FULL, "vp_rle_decompress: output buffer too small");
+	if (total == 0 || (total & 15)) return vp_fail(c, VP_ERR_ARG, "vp_rle_decompress: decoded length must be a non-zero multiple of 16");
+	if ((size_t)n_words * 4 > c->cfg.rle_arena_bytes) return vp_fail(c, VP_ERR_ARENA_FULL, "vp_rle_decompress: rle arena too small");
+	int rc = dio_reserve(c, (size_t)total + 64);
+	if (rc) return rc;
+	unsigned long long h_off[2] = {0, n_words};
+	unsigned long long *d_off = reinterpret_cast<unsigned long long *>(c->d_io);
+	uint32_t *d_status = reinterpret_cast<uint32_t *>(c->d_io + 16);
+	uint8_t *d_dst = c->d_io + 64;
+	VP_CUDA(c, cudaMemcpyAsync(c->d_rle_arena, words, (size_t)n_words * 4, cudaMemcpyHostToDevice, c->stream));
+	VP_CUDA(c, cudaMemcpyAsync(d_off, h_off, 16, cudaMemcpyHostToDevice, c->stream));
+	VP_CUDA(c, cudaMemsetAsync(d_status, 0, 4, c->stream));
+	VP_CUDA(c, vp_launch_rle_decode(reinterpret_cast<const uint32_t *>(c->d_rle_arena), d_off, nullptr, 1, d_dst, (uint32_t)total, d_status, c->stream));
+	c->launches++;
+	uint32_t status = 0;
+	VP_CUDA(c, cudaMemcpyAsync(&status, d_status, 4, cudaMemcpyDeviceToHost, c->stream));
+	VP_CUDA(c, cudaMemcpyAsync(out, d_dst, total, cudaMemcpyDeviceToHost, c->stream));
+	VP_CUDA(c, cudaStreamSynchronize(c->stream));
+	if (status) return vp_fail(c, VP_ERR_RLE, "vp_rle_decompress: malformed stream");
+	return VP_OK;
+}

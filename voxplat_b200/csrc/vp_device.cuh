@@ -1,0 +1,86 @@
+// vp_device.cuh -- device-side helpers shared by the kernels: PTX wrappers for mbarrier + TMA bulk
+// copies (cp.async.bulk -> SASS UBLKCP), byte->bit packing, bit-pair compression, shadow sampling.
+#pragma once
+#include "vp_internal.h"
+
+namespace vp {
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init()
+{
+	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+	uint32_t ok, a = smem_u32(bar);
+	do {
+		asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+		             : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+	} while (!ok);
+}
+// 1-D TMA bulk copy global -> shared, completion signalled on an mbarrier (bytes % 16 == 0, 16 B aligned).
+__device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar)
+{
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+	             ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// 4 bytes -> 4 bits (bit k = byte k != 0).
+__device__ __forceinline__ uint32_t nz4(uint32_t w)
+{
+	uint32_t t = (((w & 0x7f7f7f7fu) + 0x7f7f7f7fu) | w) & 0x80808080u;    // bit 7 of each byte = byte != 0
+	return (((t >> 7) * 0x00204081u) >> 21) & 0xFu;                        // gather bits 0,8,16,24 -> 0..3
+}
+// 16 bytes -> 16 bits.
+__device__ __forceinline__ uint32_t nz16(uint4 v)
+{
+	return nz4(v.x) | (nz4(v.y) << 4) | (nz4(v.z) << 8) | (nz4(v.w) << 12);
+}
+
+// OR adjacent bit pairs and pack the 32 results into the low half: out bit k = in bit 2k | in bit 2k+1.
+__device__ __forceinline__ uint64_t pair_or_compress(uint64_t a)
+{
+	uint64_t b = (a | (a >> 1)) & 0x5555555555555555ull;
+	b = (b | (b >> 1)) & 0x3333333333333333ull;
+	b = (b | (b >> 2)) & 0x0f0f0f0f0f0f0f0full;
+	b = (b | (b >> 4)) & 0x00ff00ff00ff00ffull;
+	b = (b | (b >> 8)) & 0x0000ffff0000ffffull;
+	b = (b | (b >> 16)) & 0x00000000ffffffffull;
+	return b;
+}
+
+// shadow_sample / shadow_sample_normal (reference shadow.h:45-75) on the device copy of the map.
+// second = +1 (sample) or -1 (sample_normal).  All arithmetic is uint32 like the reference; y+1 == 0
+// can only compare false, so the result is 1 without a load (frozen reference behaviours).
+__device__ __forceinline__ int shadow_pair(const VpWorldDev &w, uint32_t x, uint32_t y, uint32_t z, int second)
+{
+	uint32_t lim = y + 1u;
+	if (lim == 0) return 1;
+	size_t idx = (size_t)(x + y) + (size_t)w.sh_w * (size_t)(z - w.sh_z0);
+	uint32_t a = __ldg(w.shadow + idx), b = __ldg(w.shadow + idx + second);
+	return !(a < lim && b < lim);
+}
+
+// Slot of chunk (cx,cy,cz); -1 for null chunks, chunks outside the world (mesher.c:393-394) and rows not
+// held by this device.
+__device__ __forceinline__ int chunk_slot(const VpWorldDev &w, int cx, int cy, int cz)
+{
+	if ((unsigned)cx >= (1u << w.bits[0]) || (unsigned)cy >= (1u << w.bits[1]) || (unsigned)cz >= (1u << w.bits[2])) return -1;
+	if (cz < w.ez0 || cz >= w.ez1) return -1;
+	return __ldg(w.slot + ((((size_t)(cz - w.ez0) << w.bits[1]) | (unsigned)cy) << w.bits[0] | (unsigned)cx));
+}
+
+} // namespace vp

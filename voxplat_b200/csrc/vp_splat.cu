@@ -1,0 +1,541 @@
+// vp_splat.cu -- cull + 5-level LOD + splat-list emission for a batch of chunks, one kernel.
+//
+// Replaces, byte for byte, the splat branch of the reference dispatcher (chunkset.c:371-458):
+//   chunk_make_mask (mesher.c:377-456) -> chunk_make_splatlist level 0 (mesher.c:497-536)
+//   -> 4 x { chunk_mask_downsample (mesher.c:460-493) ; chunk_make_splatlist }
+//
+// Work decomposition: one thread-block CLUSTER per chunk, one CTA per 16-slice
+// z-slab of the chunk (cluster size R/16 = 1/2/4/8).  Each CTA
+//   1. streams its slab (+ the slice below and above) through a ring of shared-memory tiles with 1-D TMA
+//      bulk copies (cp.async.bulk + mbarrier), plus the +x / +y halo bytes of the neighbour chunks;
+//   2. packs bytes into 64-bit occupancy rows (bit x of row (z,y));
+//   3. derives the visibility rows with shift / AND-NOT face tests, then the 4 LOD levels by
+//      pair-OR-compress of the bit rows -- no byte mask is ever materialised;
+//   4. counts rows with popc, block-scans the counts (stable z,y,x order), exchanges the 5 per-level
+//      counts with the other CTAs of the cluster through distributed shared memory, reserves the
+//      chunk's contiguous [L0|L1|L2|L3|L4] buffer in the arena with one atomicAdd per chunk;
+//   5. emits: position from the bit index, colour byte gathered from L2 (for LOD>=1 the colour of the
+//      "last non-zero child in scan order", found by descending the bit pyramids), shadow bit from
+//      two uint16 loads.
+#include "vp_device.cuh"
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
+using namespace vp;
+
+namespace {
+
+constexpr int kConsumerWarps = 8;
+constexpr int kThreads = (kConsumerWarps + 1) * 32;     // + 1 producer warp
+constexpr int kRing = 8;                                // tiles in the TMA ring
+
+template <int RB> struct Geo {
+	static constexpr int R = 1 << RB;
+	static constexpr int ZS = 16;                        // z slices per CTA
+	static constexpr int CL = R / ZS;                    // CTAs per chunk (cluster size)
+	static constexpr int NW = R > 64 ? R / 64 : 1;       // 64-bit words per level-0 row
+	static constexpr int SLICE = R * R;
+	static constexpr int TILE = SLICE < 4096 ? SLICE : 4096;
+	static constexpr int TPS = SLICE / TILE;             // tiles per slice
+	static constexpr int RPT = TILE / R;                 // rows per tile
+	static constexpr int NSL = ZS + 2;                   // slices streamed: z0-1 .. z0+ZS
+	static constexpr int NT = NSL * TPS;
+	static constexpr int LPR = R / 16;                   // lanes (16 B each) per row
+	__host__ __device__ static constexpr int Rl(int l) { return R >> l; }
+	__host__ __device__ static constexpr int Zl(int l) { return ZS >> l; }
+	__host__ __device__ static constexpr int NWl(int l) { return Rl(l) > 64 ? Rl(l) / 64 : 1; }
+	// level bit arrays (64-bit words): main[Zl][Rl+1][NWl] (row Rl = +y plane), xpl[Zl][NWl], zpl[Rl][NWl]
+	__host__ __device__ static constexpr int main_words(int l) { return Zl(l) * (Rl(l) + 1) * NWl(l); }
+	__host__ __device__ static constexpr int xpl_off(int l) { return main_words(l); }
+	__host__ __device__ static constexpr int zpl_off(int l) { return main_words(l) + Zl(l) * NWl(l); }
+	__host__ __device__ static constexpr int lvl_words(int l) { return zpl_off(l) + Rl(l) * NWl(l); }
+	__host__ __device__ static constexpr int lvl_off(int l) { return l == 0 ? 0 : lvl_off(l - 1) + lvl_words(l - 1); }
+	static constexpr int LV_WORDS = lvl_off(5);
+	// rows in emission order: Zl*(Rl+1) slab rows, then Rl rows of the +z plane (top CTA only)
+	__host__ __device__ static constexpr int nrows(int l) { return Zl(l) * (Rl(l) + 1) + Rl(l); }
+	__host__ __device__ static constexpr int row_off(int l) { return l == 0 ? 0 : row_off(l - 1) + nrows(l - 1); }
+	static constexpr int TR = row_off(5);
+	// shared memory carve-up (bytes)
+	static constexpr int RING_BYTES = kRing * TILE;
+	static constexpr int ROW_BYTES = (TR + 1) * 4;
+	static constexpr int SCRATCH0 = ((RING_BYTES > ROW_BYTES ? RING_BYTES : ROW_BYTES) + 127) / 128 * 128;   // ring, later the row prefix
+	static constexpr int HALO_BYTES = 2 * ZS * R;
+	static constexpr int OCC_WORDS = NSL * (R + 1) * NW;
+	static constexpr int OCCX_WORDS = ZS * NW;
+	static constexpr int OFF_HALO = SCRATCH0;
+	static constexpr int OFF_OCC = OFF_HALO + HALO_BYTES;
+	static constexpr int OFF_OCCX = OFF_OCC + OCC_WORDS * 8;
+	static constexpr int OFF_LV = OFF_OCCX + OCCX_WORDS * 8;
+	static constexpr int OFF_BARS = OFF_LV + LV_WORDS * 8;
+	static constexpr int OFF_MISC = OFF_BARS + (2 * kRing + 1) * 8;
+	static constexpr int SMEM = OFF_MISC + 256;
+};
+
+struct Misc {                       // small per-CTA scalars in shared memory
+	uint32_t cnt[5];                // this CTA's splat count per level (read by cluster peers)
+	uint32_t wsum[kConsumerWarps + 1];
+	uint32_t base[5];               // first splat of this CTA's part of level l, relative to the chunk buffer
+	uint32_t total;                 // splats of the whole chunk
+	unsigned long long chunk_off;   // byte offset of the chunk buffer in the arena (~0 = not reserved)
+};
+
+enum CellKind { MAIN = 0, XPL = 1, YPL = 2, ZPL = 3 };
+
+template <int RB> struct Ctx {
+	using G = Geo<RB>;
+	const VpWorldDev &w;
+	const uint64_t *lv;             // level bit arrays
+	const uint8_t *own, *nbx_xlo, *nby, *nbz;     // chunk bytes (may be null)
+	int z0;
+	uint32_t ox, oy, oz;            // chunk origin in world voxels
+
+	__device__ __forceinline__ const uint64_t *mainrow(int l, int Z, int Y) const { return lv + G::lvl_off(l) + (Z * (G::Rl(l) + 1) + Y) * G::NWl(l); }
+	__device__ __forceinline__ const uint64_t *xpl(int l, int Z) const { return lv + G::lvl_off(l) + G::xpl_off(l) + Z * G::NWl(l); }
+	__device__ __forceinline__ const uint64_t *zpl(int l, int Y) const { return lv + G::lvl_off(l) + G::zpl_off(l) + Y * G::NWl(l); }
+
+	__device__ __forceinline__ static uint32_t pair_at(const uint64_t *row, int bit) { return (uint32_t)(row[bit >> 6] >> (bit & 63)) & 3u; }
+
+	// Colour of a level-l cell = value of its last non-zero child in (z,y,x) scan order, recursively
+	// (mesher.c:474-490): descend the bit pyramids taking the highest-priority set child each level.
+	__device__ uint8_t colour(int kind, int l, int X, int Y, int Z) const
+	{
+		for (int k = l; k >= 1; --k) {
+			const int c = k - 1;
+			if (kind == MAIN) {
+				bool found = false;
+				#pragma unroll
+				for (int d = 3; d >= 0 && !found; --d) {
+					uint32_t p = pair_at(mainrow(c, 2 * Z + (d >> 1), 2 * Y + (d & 1)), 2 * X);
+					if (p) { Z = 2 * Z + (d >> 1); Y = 2 * Y + (d & 1); X = 2 * X + (p >> 1); found = true; }
+				}
+			} else if (kind == XPL) {
+				uint32_t p = pair_at(xpl(c, 2 * Z + 1), 2 * Y);
+				if (p) { Z = 2 * Z + 1; } else { p = pair_at(xpl(c, 2 * Z), 2 * Y); Z = 2 * Z; }
+				Y = 2 * Y + (p >> 1);
+			} else if (kind == YPL) {
+				uint32_t p = pair_at(mainrow(c, 2 * Z + 1, G::Rl(c)), 2 * X);
+				if (p) { Z = 2 * Z + 1; } else { p = pair_at(mainrow(c, 2 * Z, G::Rl(c)), 2 * X); Z = 2 * Z; }
+				X = 2 * X + (p >> 1);
+			} else {
+				uint32_t p = pair_at(zpl(c, 2 * Y + 1), 2 * X);
+				if (p) { Y = 2 * Y + 1; } else { p = pair_at(zpl(c, 2 * Y), 2 * X); Y = 2 * Y; }
+				X = 2 * X + (p >> 1);
+			}
+		}
+		constexpr int R = G::R;
+		const uint8_t *p;
+		if (kind == MAIN) p = own + ((size_t)(z0 + Z) * R + Y) * R + X;
+		else if (kind == XPL) p = nbx_xlo + (size_t)(z0 + Z) * R + Y;
+		else if (kind == YPL) p = nby + (size_t)(z0 + Z) * R * R + X;
+		else p = nbz + (size_t)Y * R + X;
+		return __ldg(p);
+	}
+
+	// One splat: int16 x,y,z = origin + (cell << l); int16 colour | shadow << 6, shadow sampled at
+	// +(1<<l) on every axis for l > 0 (mesher.c:521-531).  (X,Y,Zc) are level-l cell coordinates in the
+	// chunk (the halo index is R>>l).
+	__device__ __forceinline__ void emit(unsigned long long *dst, int kind, int l, int X, int Y, int Zloc, int Zc) const
+	{
+		uint32_t c = colour(kind, l, X, Y, Zloc);
+		uint32_t wx = ox + ((uint32_t)X << l), wy = oy + ((uint32_t)Y << l), wz = oz + ((uint32_t)Zc << l);
+		uint32_t d = l ? (1u << l) : 0u;
+		uint32_t sh = (uint32_t)shadow_pair(w, wx + d, wy + d, wz + d, 1);
+		uint32_t col = (c | (sh << 6)) & 0xFFFFu;
+		*dst = (unsigned long long)(wx & 0xFFFFu) | ((unsigned long long)(wy & 0xFFFFu) << 16)
+		     | ((unsigned long long)(wz & 0xFFFFu) << 32) | ((unsigned long long)col << 48);
+	}
+};
+
+template <int RB>
+__global__ void __launch_bounds__(kThreads)
+k_splat(const VpWorldDev w, const uint32_t *__restrict__ ids, VpResultDev *__restrict__ results,
+        const uint32_t *__restrict__ result_pos, uint8_t *__restrict__ arena, VpArenaDev *__restrict__ st)
+{
+	using G = Geo<RB>;
+	constexpr int R = G::R, ZS = G::ZS, CL = G::CL, NW = G::NW, TILE = G::TILE, TPS = G::TPS, NT = G::NT;
+	extern __shared__ __align__(128) uint8_t smem[];
+	uint8_t *ring = smem;
+	uint32_t *rowpre = reinterpret_cast<uint32_t *>(smem);                 // aliases the ring after phase 1
+	uint8_t *halo = smem + G::OFF_HALO;
+	uint64_t *occ = reinterpret_cast<uint64_t *>(smem + G::OFF_OCC);
+	uint64_t *occx = reinterpret_cast<uint64_t *>(smem + G::OFF_OCCX);
+	uint64_t *lv = reinterpret_cast<uint64_t *>(smem + G::OFF_LV);
+	uint64_t *bar_full = reinterpret_cast<uint64_t *>(smem + G::OFF_BARS);
+	uint64_t *bar_empty = bar_full + kRing;
+	uint64_t *bar_halo = bar_empty + kRing;
+	Misc *misc = reinterpret_cast<Misc *>(smem + G::OFF_MISC);
+
+	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+	const int crank = CL > 1 ? (int)(blockIdx.x % CL) : 0;
+	const uint32_t chunk_i = blockIdx.x / CL;
+	const uint32_t cid = ids[chunk_i];
+	const int cx = (int)(cid & ((1u << w.bits[0]) - 1)), cy = (int)((cid >> w.bits[0]) & ((1u << w.bits[1]) - 1));
+	const int cz = (int)(cid >> (w.bits[0] + w.bits[1]));
+	const int z0 = crank * ZS;
+	const bool top = (z0 + ZS == R);
+
+	const int s_own = chunk_slot(w, cx, cy, cz), s_x = chunk_slot(w, cx + 1, cy, cz);
+	const int s_y = chunk_slot(w, cx, cy + 1, cz), s_z = chunk_slot(w, cx, cy, cz + 1);
+	const size_t N = (size_t)R * R * R;
+	const uint8_t *own = s_own >= 0 ? w.vox_pool + (size_t)s_own * N : nullptr;
+	const uint8_t *nbx_xlo = s_x >= 0 ? w.xlo_pool + (size_t)s_x * R * R : nullptr;
+	const uint8_t *nby = s_y >= 0 ? w.vox_pool + (size_t)s_y * N : nullptr;
+	const uint8_t *nbz = s_z >= 0 ? w.vox_pool + (size_t)s_z * N : nullptr;
+	VpResultDev *res = results + (result_pos ? result_pos[chunk_i] : chunk_i);
+
+	if (!own && !nbx_xlo && !nby && !nbz) {           // mesher.c:404-409: nothing can be visible
+		if (crank == 0 && tid == 0) {
+			res->svl_offset = 0;
+			for (int l = 0; l < 5; l++) res->svl_items[l] = 0;
+			res->svl_items_total = 0;
+		}
+		return;                                        // uniform over the whole cluster
+	}
+
+	// ---- phase 0: barriers, zero the bit arrays ---------------------------------------------------
+	if (tid == 0) {
+		for (int i = 0; i < kRing; i++) { mbar_init(bar_full + i, 1); mbar_init(bar_empty + i, 1); }
+		mbar_init(bar_halo, 1);
+		mbar_fence_init();
+	}
+	for (int i = tid; i < G::OCC_WORDS + G::OCCX_WORDS + G::LV_WORDS; i += kThreads) occ[i] = 0;   // occ, occx, lv are contiguous
+	__syncthreads();
+
+	// source of streamed slice s (z = z0 - 1 + s); nullptr = air or not needed
+	auto slice_src = [&](int s) -> const uint8_t * {
+		int z = z0 - 1 + s;
+		if (z < 0) return nullptr;                     // no -z test at z = 0 (pair walk starts at A, mesher.c:421)
+		if (z < R) return own ? own + (size_t)z * R * R : nullptr;
+		return nbz;                                    // z == R: slice 0 of the +z neighbour
+	};
+	const bool have_halo = nbx_xlo || nby;
+
+	// ---- phase 1: TMA producer (warp 8) / byte->bit consumers (warps 0..7) -------------------------
+	if (warp == kConsumerWarps) {
+		if (lane == 0) {
+			if (have_halo) {
+				mbar_arrive_expect_tx(bar_halo, (nbx_xlo ? ZS * R : 0) + (nby ? ZS * R : 0));
+				if (nbx_xlo) tma_load_1d(halo, nbx_xlo + (size_t)z0 * R, ZS * R, bar_halo);
+				if (nby) for (int z = 0; z < ZS; z++) tma_load_1d(halo + ZS * R + z * R, nby + (size_t)(z0 + z) * R * R, R, bar_halo);
+			}
+			for (int t = 0; t < NT; t++) {
+				const int b = t % kRing, u = t / kRing;
+				if (u > 0) mbar_wait(bar_empty + b, (u - 1) & 1);
+				const uint8_t *src = slice_src(t / TPS);
+				if (src) {
+					mbar_arrive_expect_tx(bar_full + b, TILE);
+					tma_load_1d(ring + b * TILE, src + (size_t)(t % TPS) * TILE, TILE, bar_full + b);
+				} else {
+					mbar_arrive(bar_full + b);          // keep the phases aligned, nothing to load
+				}
+			}
+		}
+	} else {
+		for (int t = warp; t < NT; t += kConsumerWarps) {
+			const int b = t % kRing, u = t / kRing, s = t / TPS, part = t % TPS;
+			mbar_wait(bar_full + b, u & 1);
+			if (slice_src(s)) {
+				const uint8_t *tb = ring + b * TILE;
+				uint64_t *orow = occ + (size_t)(s * (R + 1) + part * G::RPT) * NW;
+				#pragma unroll 4
+				for (int off = lane * 16; off < TILE; off += 512) {
+					uint32_t m = nz16(*reinterpret_cast<const uint4 *>(tb + off));
+					const int row = off / R, bo = off % R;
+					if (R >= 32) {
+						uint32_t v = m << (bo & 16);
+						v |= __shfl_xor_sync(0xffffffffu, v, 1);
+						if (!(lane & 1)) reinterpret_cast<uint32_t *>(orow + row * NW)[bo >> 5] = v;
+					} else {
+						reinterpret_cast<uint32_t *>(orow + row * NW)[0] = m;
+					}
+				}
+			}
+			__syncwarp();
+			if (lane == 0) mbar_arrive(bar_empty + b);
+		}
+		// halo rows: 0..ZS-1 = x = 0 column of the +x neighbour (bits over y), ZS..2ZS-1 = y = 0 row of +y
+		if (have_halo) {
+			mbar_wait(bar_halo, 0);
+			for (int f = tid; f < 2 * ZS * G::LPR; f += kConsumerWarps * 32) {
+				const int hr = f / G::LPR, bo = (f % G::LPR) * 16;
+				const bool isx = hr < ZS;
+				if (isx ? (nbx_xlo != nullptr) : (nby != nullptr)) {
+					uint32_t m = nz16(*reinterpret_cast<const uint4 *>(halo + hr * R + bo));
+					uint64_t *dst = isx ? occx + hr * NW : occ + (size_t)((hr - ZS + 1) * (R + 1) + R) * NW;
+					if (R >= 32) {
+						uint32_t v = m << (bo & 16);
+						v |= __shfl_xor_sync(0xffffffffu, v, 1);
+						if (!(lane & 1)) reinterpret_cast<uint32_t *>(dst)[bo >> 5] = v;
+					} else {
+						reinterpret_cast<uint32_t *>(dst)[0] = m;
+					}
+				}
+			}
+		}
+	}
+	__syncthreads();
+
+	// ---- phase 2: visibility rows (closed form of the pair walk, mesher.c:421-448) -------------------
+	uint64_t *lv0 = lv;
+	for (int f0 = warp * 32; f0 < ZS * R; f0 += (kThreads / 32) * 32) {
+		const int f = f0 + lane, zi = f >> RB, y = f & (R - 1), s = zi + 1;
+		const uint64_t *o = occ + (size_t)(s * (R + 1) + y) * NW;
+		const uint64_t xbit = (occx[zi * NW + (y >> 6)] >> (y & 63)) & 1ull;
+		#pragma unroll
+		for (int k = 0; k < NW; k++) {
+			const uint64_t ow = o[k];
+			const uint64_t nxt = (k + 1 < NW) ? (o[k + 1] & 1ull) : xbit;
+			const uint64_t px = (ow >> 1) | (nxt << ((R - 1) & 63));
+			const uint64_t mx = (ow << 1) | (k > 0 ? (o[k - 1] >> 63) : 1ull);
+			const uint64_t py = o[NW + k];
+			const uint64_t my = y > 0 ? o[k - NW] : ~0ull;
+			const uint64_t pz = occ[(size_t)((s + 1) * (R + 1) + y) * NW + k];
+			const uint64_t mz = (z0 + zi) > 0 ? occ[(size_t)((s - 1) * (R + 1) + y) * NW + k] : ~0ull;
+			lv0[(zi * (R + 1) + y) * NW + k] = ow & ~(px & mx & py & my & pz & mz);
+		}
+		const uint32_t vx = (uint32_t)(xbit & ~(o[NW - 1] >> ((R - 1) & 63)));
+		const uint32_t bal = __ballot_sync(0xffffffffu, vx & 1u);
+		uint64_t *xp = lv0 + G::xpl_off(0);
+		if (R >= 32) { if (lane == 0) reinterpret_cast<uint32_t *>(xp + zi * NW)[y >> 5] = bal; }
+		else if ((lane & 15) == 0) xp[zi] = (bal >> lane) & 0xFFFFu;
+	}
+	for (int f = tid; f < (ZS + (top && nbz ? R : 0)) * NW; f += kThreads) {
+		const int r = f / NW, k = f % NW;
+		if (r < ZS) {            // +y plane row of slice r: solid in the neighbour, air below it in this chunk
+			const uint64_t *o = occ + (size_t)((r + 1) * (R + 1)) * NW;
+			lv0[(r * (R + 1) + R) * NW + k] = o[R * NW + k] & ~o[(R - 1) * NW + k];
+		} else {                 // +z plane row y = r - ZS
+			const int y = r - ZS;
+			lv0[G::zpl_off(0) + y * NW + k] = occ[(size_t)((ZS + 1) * (R + 1) + y) * NW + k] & ~occ[(size_t)(ZS * (R + 1) + y) * NW + k];
+		}
+	}
+	__syncthreads();
+
+	// ---- phase 3: LOD pyramids, level l from l-1 by OR of the child rows + pair-OR-compress ---------
+	#pragma unroll
+	for (int l = 1; l < 5; l++) {
+		const int c = l - 1;
+		const int Rl = G::Rl(l), Zl = G::Zl(l), Rc = G::Rl(c), NWc = G::NWl(c);
+		const uint64_t *cm = lv + G::lvl_off(c);
+		uint64_t *pm = lv + G::lvl_off(l);
+		const int n_main = Zl * (Rl + 1), n_all = n_main + Zl + Rl;
+		for (int g = tid; g < n_all; g += kThreads) {
+			uint64_t a0 = 0, a1 = 0;
+			uint64_t *dst;
+			if (g < n_main) {
+				const int Z = g / (Rl + 1), Y = g % (Rl + 1);
+				for (int dz = 0; dz < 2; dz++) {
+					if (Y < Rl) {
+						for (int dy = 0; dy < 2; dy++) {
+							const uint64_t *r = cm + (size_t)((2 * Z + dz) * (Rc + 1) + 2 * Y + dy) * NWc;
+							a0 |= r[0]; if (NWc > 1) a1 |= r[NWc - 1];
+						}
+					} else {
+						const uint64_t *r = cm + (size_t)((2 * Z + dz) * (Rc + 1) + Rc) * NWc;
+						a0 |= r[0]; if (NWc > 1) a1 |= r[NWc - 1];
+					}
+				}
+				dst = pm + g;
+			} else if (g < n_main + Zl) {
+				const int Z = g - n_main;
+				const uint64_t *r = cm + G::xpl_off(c) + (size_t)(2 * Z) * NWc;
+				a0 = r[0] | r[NWc]; if (NWc > 1) a1 = r[NWc - 1] | r[2 * NWc - 1];
+				dst = pm + G::xpl_off(l) + Z;
+			} else {
+				const int Y = g - n_main - Zl;
+				const uint64_t *r = cm + G::zpl_off(c) + (size_t)(2 * Y) * NWc;
+				a0 = r[0] | r[NWc]; if (NWc > 1) a1 = r[NWc - 1] | r[2 * NWc - 1];
+				dst = pm + G::zpl_off(l) + Y;
+			}
+			uint64_t p = pair_or_compress(a0);
+			if (NWc > 1) p |= pair_or_compress(a1) << 32;
+			*dst = p;                                      // NWl(l) == 1 for every l >= 1 (R <= 128)
+		}
+		__syncthreads();
+	}
+
+	// ---- phase 4: per-row counts (popc) and their exclusive prefix = stable (z,y,x) ranks -----------
+	for (int r = tid; r < G::TR; r += kThreads) {
+		int l = 0;
+		#pragma unroll
+		for (int k = 1; k < 5; k++) if (r >= G::row_off(k)) l = k;
+		const int q = r - G::row_off(l), Rl = G::Rl(l), NWl = G::NWl(l), n_main = G::Zl(l) * (Rl + 1);
+		const uint64_t *base = lv + G::lvl_off(l);
+		uint32_t c = 0;
+		if (q < n_main) {
+			const int Z = q / (Rl + 1), Y = q % (Rl + 1);
+			for (int k = 0; k < NWl; k++) c += __popcll(base[q * NWl + k]);
+			if (Y < Rl) c += (uint32_t)(base[G::xpl_off(l) + Z * NWl + (Y >> 6)] >> (Y & 63)) & 1u;
+		} else {
+			const int Y = q - n_main;
+			for (int k = 0; k < NWl; k++) c += __popcll(base[G::zpl_off(l) + Y * NWl + k]);    // zero unless top
+		}
+		rowpre[r] = c;
+	}
+	__syncthreads();
+	{
+		constexpr int IPT = (G::TR + kThreads - 1) / kThreads;
+		const int b0 = tid * IPT, b1 = min(b0 + IPT, G::TR);
+		uint32_t sum = 0;
+		for (int r = b0; r < b1; r++) sum += rowpre[r];
+		uint32_t inc = sum;
+		#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
+		if (lane == 31) misc->wsum[warp] = inc;
+		__syncthreads();
+		uint32_t pre = inc - sum;
+		for (int k = 0; k < warp; k++) pre += misc->wsum[k];
+		for (int r = b0; r < b1; r++) { uint32_t c = rowpre[r]; rowpre[r] = pre; pre += c; }
+		if (tid == kThreads - 1) rowpre[G::TR] = pre;
+		__syncthreads();
+		if (tid < 5) misc->cnt[tid] = rowpre[G::row_off(tid + 1)] - rowpre[G::row_off(tid)];      // row_off(5) == TR
+	}
+
+	// ---- phase 5: cluster exchange of the counts, one arena reservation per chunk -------------------
+	if (CL > 1) {
+		cg::cluster_group cluster = cg::this_cluster();
+		cluster.sync();
+		if (tid == 0) {
+			uint32_t tot[5] = {0, 0, 0, 0, 0}, below[5] = {0, 0, 0, 0, 0};
+			for (int r = 0; r < CL; r++) {
+				const Misc *pm = cluster.map_shared_rank(misc, r);
+				for (int l = 0; l < 5; l++) { uint32_t c = pm->cnt[l]; tot[l] += c; if (r < crank) below[l] += c; }
+			}
+			uint32_t acc = 0;
+			for (int l = 0; l < 5; l++) { misc->base[l] = acc + below[l]; acc += tot[l]; }
+			misc->total = acc;
+			if (crank == 0) {
+				unsigned long long bytes = (unsigned long long)acc * 8ull, off = 0;
+				if (acc) {
+					off = atomicAdd(&st->cursor, bytes);
+					if (off + bytes > st->capacity) { atomicExch(&st->overflow, 1u); off = ~0ull; }
+				}
+				for (int r = 0; r < CL; r++) cluster.map_shared_rank(misc, r)->chunk_off = off;
+				res->svl_offset = off;
+				for (int l = 0; l < 5; l++) res->svl_items[l] = tot[l] * 4u;
+				res->svl_items_total = acc * 4u;
+			}
+		}
+		cluster.sync();
+	} else {
+		__syncthreads();
+		if (tid == 0) {
+			uint32_t acc = 0;
+			for (int l = 0; l < 5; l++) { misc->base[l] = acc; acc += misc->cnt[l]; }
+			misc->total = acc;
+			unsigned long long bytes = (unsigned long long)acc * 8ull, off = 0;
+			if (acc) {
+				off = atomicAdd(&st->cursor, bytes);
+				if (off + bytes > st->capacity) { atomicExch(&st->overflow, 1u); off = ~0ull; }
+			}
+			misc->chunk_off = off;
+			res->svl_offset = off;
+			for (int l = 0; l < 5; l++) res->svl_items[l] = misc->cnt[l] * 4u;
+			res->svl_items_total = acc * 4u;
+		}
+		__syncthreads();
+	}
+	if (misc->chunk_off == ~0ull || misc->total == 0) return;
+	unsigned long long *out = reinterpret_cast<unsigned long long *>(arena + misc->chunk_off);
+
+	Ctx<RB> cx_{w, lv, own, nbx_xlo, nby, nbz, z0, (uint32_t)cx << RB, (uint32_t)cy << RB, (uint32_t)cz << RB};
+
+	// ---- phase 6a: level 0, one warp per non-empty row, lanes over the bits (coalesced 8 B stores) ----
+	{
+		const int n_main = ZS * (R + 1), n_rows = n_main + (top ? R : 0);
+		unsigned long long *o0 = out + misc->base[0];
+		for (int r0 = warp * 32; r0 < n_rows; r0 += (kThreads / 32) * 32) {
+			const int r = r0 + lane;
+			const bool has = r < n_rows && rowpre[r + 1] != rowpre[r];
+			uint32_t todo = __ballot_sync(0xffffffffu, has);
+			while (todo) {
+				const int rr = r0 + __ffs(todo) - 1;
+				todo &= todo - 1;
+				uint32_t pos = rowpre[rr];               // row_off(0) == 0
+				int kind, Y, Zloc, Zc;
+				const uint64_t *bits;
+				if (rr < n_main) { Zloc = rr / (R + 1); Y = rr % (R + 1); Zc = z0 + Zloc; kind = Y < R ? MAIN : YPL; bits = lv0 + rr * NW; }
+				else { Y = rr - n_main; Zloc = 0; Zc = R; kind = ZPL; bits = lv0 + G::zpl_off(0) + Y * NW; }
+				const int Yc = kind == YPL ? R : Y;
+				#pragma unroll
+				for (int k = 0; k < NW; k++) {
+					const uint64_t wd = bits[k];
+					#pragma unroll
+					for (int h = 0; h < 2; h++) {
+						const int bit = h * 32 + lane;
+						if (bit < R && ((wd >> bit) & 1ull))
+							cx_.emit(o0 + pos + __popcll(wd & ((1ull << bit) - 1ull)), kind, 0, k * 64 + bit, Yc, Zloc, Zc);
+					}
+					pos += __popcll(wd);
+				}
+				if (kind == MAIN && lane == 0 && ((lv0[G::xpl_off(0) + Zloc * NW + (Y >> 6)] >> (Y & 63)) & 1ull))
+					cx_.emit(o0 + pos, XPL, 0, R, Y, Zloc, Zc);
+			}
+		}
+	}
+	// ---- phase 6b: levels 1..4, one thread per row (rows are short and few) -------------------------
+	for (int r = G::row_off(1) + tid; r < G::TR; r += kThreads) {
+		if (rowpre[r + 1] == rowpre[r]) continue;
+		int l = 1;
+		#pragma unroll
+		for (int k = 2; k < 5; k++) if (r >= G::row_off(k)) l = k;
+		const int q = r - G::row_off(l), Rl = G::Rl(l), n_main = G::Zl(l) * (Rl + 1);
+		unsigned long long *ol = out + misc->base[l] + (rowpre[r] - rowpre[G::row_off(l)]);
+		const uint64_t *base = lv + G::lvl_off(l);
+		if (q < n_main) {
+			const int Zloc = q / (Rl + 1), Y = q % (Rl + 1), Zc = (z0 >> l) + Zloc;
+			uint64_t wd = base[q];
+			const int kind = Y < Rl ? MAIN : YPL;
+			while (wd) { const int X = __ffsll((long long)wd) - 1; wd &= wd - 1; cx_.emit(ol++, kind, l, X, Y, Zloc, Zc); }
+			if (Y < Rl && ((base[G::xpl_off(l) + Zloc] >> Y) & 1ull)) cx_.emit(ol, XPL, l, Rl, Y, Zloc, Zc);
+		} else {
+			const int Y = q - n_main;
+			uint64_t wd = base[G::zpl_off(l) + Y];
+			while (wd) { const int X = __ffsll((long long)wd) - 1; wd &= wd - 1; cx_.emit(ol++, ZPL, l, X, Y, 0, Rl); }
+		}
+	}
+}
+
+template <int RB>
+cudaError_t launch(const VpWorldDev &w, const uint32_t *d_ids, uint32_t n, VpResultDev *d_results,
+                   const uint32_t *d_result_pos, uint8_t *arena, VpArenaDev *state, cudaStream_t s)
+{
+	using G = Geo<RB>;
+	static bool configured = false;
+	if (!configured) {
+		cudaError_t e = cudaFuncSetAttribute(k_splat<RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM);
+		if (e != cudaSuccess) return e;
+		configured = true;
+	}
+	cudaLaunchConfig_t cfg = {};
+	cfg.gridDim = dim3(n * G::CL);
+	cfg.blockDim = dim3(kThreads);
+	cfg.dynamicSmemBytes = G::SMEM;
+	cfg.stream = s;
+	cudaLaunchAttribute attr[1];
+	attr[0].id = cudaLaunchAttributeClusterDimension;
+	attr[0].val.clusterDim.x = G::CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+	cfg.attrs = attr;
+	cfg.numAttrs = G::CL > 1 ? 1 : 0;
+	return cudaLaunchKernelEx(&cfg, k_splat<RB>, w, d_ids, d_results, d_result_pos, arena, state);
+}
+
+} // namespace
+
+cudaError_t vp_launch_splat(const VpWorldDev &w, const uint32_t *d_ids, uint32_t n, VpResultDev *d_results,
+                            const uint32_t *d_result_pos, uint8_t *arena, VpArenaDev *state, cudaStream_t s)
+{
+	if (n == 0) return cudaSuccess;
+	switch (w.rb) {
+	case 4: return launch<4>(w, d_ids, n, d_results, d_result_pos, arena, state, s);
+	case 5: return launch<5>(w, d_ids, n, d_results, d_result_pos, arena, state, s);
+	case 6: return launch<6>(w, d_ids, n, d_results, d_result_pos, arena, state, s);
+	case 7: return launch<7>(w, d_ids, n, d_results, d_result_pos, arena, state, s);
+	default: return cudaErrorInvalidValue;
+	}
+}
+
+int vp_splat_smem_bytes(int rb)
+{
+	switch (rb) { case 4: return Geo<4>::SMEM; case 5: return Geo<5>::SMEM; case 6: return Geo<6>::SMEM; case 7: return Geo<7>::SMEM; }
+	return -1;
+}
