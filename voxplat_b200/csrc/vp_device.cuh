@@ -42,7 +42,7 @@ __device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gsrc, ui
 __device__ __forceinline__ uint32_t nz4(uint32_t w)
 {
 	uint32_t t = (((w & 0x7f7f7f7fu) + 0x7f7f7f7fu) | w) & 0x80808080u;    // bit 7 of each byte = byte != 0
-	return (((t >> 7) * 0x00204081u) >> 21) & 0xFu;                        // gather bits 0,8,16,24 -> 0..3
+	return (t * 0x00204081u) >> 28;                                        // gather bits 7,15,23,31 -> 0..3 (top nibble of the product)
 }
 // 16 bytes -> 16 bits.
 __device__ __forceinline__ uint32_t nz16(uint4 v)

@@ -68,6 +68,9 @@ template <int RB> struct Geo {
 	static constexpr int OFF_BARS = OFF_LV + LV_WORDS * 8;
 	static constexpr int OFF_MISC = OFF_BARS + (2 * kRing + 1) * 8;
 	static constexpr int SMEM = OFF_MISC + 256;
+	// entry list of phase 6: everything between the row prefix and the level bit arrays is dead by then
+	static constexpr int OFF_LIST = (ROW_BYTES + 15) / 16 * 16;
+	static constexpr int LIST_CAP = (OFF_LV - OFF_LIST) / 4;
 };
 
 struct Misc {                       // small per-CTA scalars in shared memory
@@ -80,6 +83,12 @@ struct Misc {                       // small per-CTA scalars in shared memory
 
 enum CellKind { MAIN = 0, XPL = 1, YPL = 2, ZPL = 3 };
 
+// runtime-level versions of the constexpr offset functions (select chains over compile-time constants)
+template <int RB> __device__ __forceinline__ int lvl_off_rt(int l) { using G = Geo<RB>; return l == 0 ? 0 : l == 1 ? G::lvl_off(1) : l == 2 ? G::lvl_off(2) : l == 3 ? G::lvl_off(3) : G::lvl_off(4); }
+template <int RB> __device__ __forceinline__ int row_off_rt(int l) { using G = Geo<RB>; return l == 0 ? 0 : l == 1 ? G::row_off(1) : l == 2 ? G::row_off(2) : l == 3 ? G::row_off(3) : G::row_off(4); }
+template <int RB> __device__ __forceinline__ int zpl_off_rt(int l) { using G = Geo<RB>; return l == 0 ? G::zpl_off(0) : l == 1 ? G::zpl_off(1) : l == 2 ? G::zpl_off(2) : l == 3 ? G::zpl_off(3) : G::zpl_off(4); }
+template <int RB> __device__ __forceinline__ int xpl_off_rt(int l) { using G = Geo<RB>; return l == 0 ? G::xpl_off(0) : l == 1 ? G::xpl_off(1) : l == 2 ? G::xpl_off(2) : l == 3 ? G::xpl_off(3) : G::xpl_off(4); }
+
 template <int RB> struct Ctx {
 	using G = Geo<RB>;
 	const VpWorldDev &w;
@@ -88,60 +97,74 @@ template <int RB> struct Ctx {
 	int z0;
 	uint32_t ox, oy, oz;            // chunk origin in world voxels
 
-	__device__ __forceinline__ const uint64_t *mainrow(int l, int Z, int Y) const { return lv + G::lvl_off(l) + (Z * (G::Rl(l) + 1) + Y) * G::NWl(l); }
-	__device__ __forceinline__ const uint64_t *xpl(int l, int Z) const { return lv + G::lvl_off(l) + G::xpl_off(l) + Z * G::NWl(l); }
-	__device__ __forceinline__ const uint64_t *zpl(int l, int Y) const { return lv + G::lvl_off(l) + G::zpl_off(l) + Y * G::NWl(l); }
-
 	__device__ __forceinline__ static uint32_t pair_at(const uint64_t *row, int bit) { return (uint32_t)(row[bit >> 6] >> (bit & 63)) & 3u; }
 
-	// Colour of a level-l cell = value of its last non-zero child in (z,y,x) scan order, recursively
-	// (mesher.c:474-490): descend the bit pyramids taking the highest-priority set child each level.
-	__device__ uint8_t colour(int kind, int l, int X, int Y, int Z) const
+	// One step of the descent from level K to K-1: take the highest-priority set child, i.e. the LAST
+	// non-zero child in (z,y,x) scan order (mesher.c:474-490).  All array offsets are compile-time.
+	template <int K>
+	__device__ __forceinline__ void descend(int kind, int &X, int &Y, int &Z) const
 	{
-		for (int k = l; k >= 1; --k) {
-			const int c = k - 1;
+		if constexpr (K >= 1) {
+			constexpr int c = K - 1, Rc = G::Rl(c), NWc = G::NWl(c);
+			const uint64_t *cm = lv + G::lvl_off(c);
 			if (kind == MAIN) {
-				bool found = false;
-				#pragma unroll
-				for (int d = 3; d >= 0 && !found; --d) {
-					uint32_t p = pair_at(mainrow(c, 2 * Z + (d >> 1), 2 * Y + (d & 1)), 2 * X);
-					if (p) { Z = 2 * Z + (d >> 1); Y = 2 * Y + (d & 1); X = 2 * X + (p >> 1); found = true; }
-				}
+				uint32_t p = pair_at(cm + ((2 * Z + 1) * (Rc + 1) + 2 * Y + 1) * NWc, 2 * X);
+				int dz = 1, dy = 1;
+				if (!p) { p = pair_at(cm + ((2 * Z + 1) * (Rc + 1) + 2 * Y) * NWc, 2 * X); dy = 0; }
+				if (!p) { p = pair_at(cm + ((2 * Z) * (Rc + 1) + 2 * Y + 1) * NWc, 2 * X); dz = 0; dy = 1; }
+				if (!p) { p = pair_at(cm + ((2 * Z) * (Rc + 1) + 2 * Y) * NWc, 2 * X); dy = 0; }
+				Z = 2 * Z + dz; Y = 2 * Y + dy; X = 2 * X + (int)(p >> 1);
 			} else if (kind == XPL) {
-				uint32_t p = pair_at(xpl(c, 2 * Z + 1), 2 * Y);
-				if (p) { Z = 2 * Z + 1; } else { p = pair_at(xpl(c, 2 * Z), 2 * Y); Z = 2 * Z; }
-				Y = 2 * Y + (p >> 1);
+				uint32_t p = pair_at(cm + G::xpl_off(c) + (2 * Z + 1) * NWc, 2 * Y);
+				if (p) { Z = 2 * Z + 1; } else { p = pair_at(cm + G::xpl_off(c) + (2 * Z) * NWc, 2 * Y); Z = 2 * Z; }
+				Y = 2 * Y + (int)(p >> 1);
 			} else if (kind == YPL) {
-				uint32_t p = pair_at(mainrow(c, 2 * Z + 1, G::Rl(c)), 2 * X);
-				if (p) { Z = 2 * Z + 1; } else { p = pair_at(mainrow(c, 2 * Z, G::Rl(c)), 2 * X); Z = 2 * Z; }
-				X = 2 * X + (p >> 1);
+				uint32_t p = pair_at(cm + ((2 * Z + 1) * (Rc + 1) + Rc) * NWc, 2 * X);
+				if (p) { Z = 2 * Z + 1; } else { p = pair_at(cm + ((2 * Z) * (Rc + 1) + Rc) * NWc, 2 * X); Z = 2 * Z; }
+				X = 2 * X + (int)(p >> 1);
 			} else {
-				uint32_t p = pair_at(zpl(c, 2 * Y + 1), 2 * X);
-				if (p) { Y = 2 * Y + 1; } else { p = pair_at(zpl(c, 2 * Y), 2 * X); Y = 2 * Y; }
-				X = 2 * X + (p >> 1);
+				uint32_t p = pair_at(cm + G::zpl_off(c) + (2 * Y + 1) * NWc, 2 * X);
+				if (p) { Y = 2 * Y + 1; } else { p = pair_at(cm + G::zpl_off(c) + (2 * Y) * NWc, 2 * X); Y = 2 * Y; }
+				X = 2 * X + (int)(p >> 1);
 			}
+			descend<K - 1>(kind, X, Y, Z);
 		}
-		constexpr int R = G::R;
-		const uint8_t *p;
-		if (kind == MAIN) p = own + ((size_t)(z0 + Z) * R + Y) * R + X;
-		else if (kind == XPL) p = nbx_xlo + (size_t)(z0 + Z) * R + Y;
-		else if (kind == YPL) p = nby + (size_t)(z0 + Z) * R * R + X;
-		else p = nbz + (size_t)Y * R + X;
-		return __ldg(p);
 	}
 
-	// One splat: int16 x,y,z = origin + (cell << l); int16 colour | shadow << 6, shadow sampled at
-	// +(1<<l) on every axis for l > 0 (mesher.c:521-531).  (X,Y,Zc) are level-l cell coordinates in the
-	// chunk (the halo index is R>>l).
-	__device__ __forceinline__ void emit(unsigned long long *dst, int kind, int l, int X, int Y, int Zloc, int Zc) const
+	// One splat of level L: int16 x,y,z = origin + (cell << L); int16 colour | shadow << 6, the shadow
+	// sampled at +(1<<L) on every axis for L > 0 (mesher.c:521-531).  (X,Y,Zc) are level-L cell
+	// coordinates in the chunk (the halo index is R>>L); Zloc is the cell's z index inside this CTA's slab.
+	template <int L>
+	__device__ __forceinline__ void emit(unsigned long long *dst, int kind, int X, int Y, int Zloc, int Zc) const
 	{
-		uint32_t c = colour(kind, l, X, Y, Zloc);
-		uint32_t wx = ox + ((uint32_t)X << l), wy = oy + ((uint32_t)Y << l), wz = oz + ((uint32_t)Zc << l);
-		uint32_t d = l ? (1u << l) : 0u;
-		uint32_t sh = (uint32_t)shadow_pair(w, wx + d, wy + d, wz + d, 1);
-		uint32_t col = (c | (sh << 6)) & 0xFFFFu;
-		*dst = (unsigned long long)(wx & 0xFFFFu) | ((unsigned long long)(wy & 0xFFFFu) << 16)
-		     | ((unsigned long long)(wz & 0xFFFFu) << 32) | ((unsigned long long)col << 48);
+		const uint32_t wx = ox + ((uint32_t)X << L), wy = oy + ((uint32_t)Y << L), wz = oz + ((uint32_t)Zc << L);
+		constexpr uint32_t d = L ? (1u << L) : 0u;
+		const uint32_t sh = (uint32_t)shadow_pair(w, wx + d, wy + d, wz + d, 1);
+		int cxx = X, cyy = Y, czz = Zloc;
+		descend<L>(kind, cxx, cyy, czz);
+		constexpr int R = G::R;
+		const uint8_t *p;
+		if (kind == MAIN) p = own + ((size_t)(z0 + czz) * R + cyy) * R + cxx;
+		else if (kind == XPL) p = nbx_xlo + (size_t)(z0 + czz) * R + cyy;
+		else if (kind == YPL) p = nby + (size_t)(z0 + czz) * R * R + cxx;
+		else p = nbz + (size_t)cyy * R + cxx;
+		const uint32_t col = ((uint32_t)__ldg(p) | (sh << 6)) & 0xFFFFu;
+		const uint32_t lo = (wx & 0xFFFFu) | (wy << 16), hi = (wz & 0xFFFFu) | (col << 16);
+		*reinterpret_cast<uint2 *>(dst) = make_uint2(lo, hi);
+	}
+
+	// Emit list entry `ent` = (row << 8 | x) of level L; q = row index inside the level.
+	template <int L>
+	__device__ __forceinline__ void emit_entry(unsigned long long *dst, int q, int x) const
+	{
+		constexpr int Rl = G::Rl(L), n_main = G::Zl(L) * (Rl + 1);
+		if (q < n_main) {
+			const int Zloc = q / (Rl + 1), Y = q - Zloc * (Rl + 1);
+			const int kind = Y == Rl ? YPL : (x == Rl ? XPL : MAIN);
+			emit<L>(dst, kind, x, Y, Zloc, (z0 >> L) + Zloc);
+		} else {
+			emit<L>(dst, ZPL, x, q - n_main, 0, Rl);
+		}
 	}
 };
 
@@ -358,16 +381,16 @@ k_splat(const VpWorldDev w, const uint32_t *__restrict__ ids, VpResultDev *__res
 		int l = 0;
 		#pragma unroll
 		for (int k = 1; k < 5; k++) if (r >= G::row_off(k)) l = k;
-		const int q = r - G::row_off(l), Rl = G::Rl(l), NWl = G::NWl(l), n_main = G::Zl(l) * (Rl + 1);
-		const uint64_t *base = lv + G::lvl_off(l);
+		const int q = r - row_off_rt<RB>(l), Rl = R >> l, NWl = l == 0 ? NW : 1, n_main = (ZS >> l) * (Rl + 1);
+		const uint64_t *base = lv + lvl_off_rt<RB>(l);
 		uint32_t c = 0;
 		if (q < n_main) {
 			const int Z = q / (Rl + 1), Y = q % (Rl + 1);
 			for (int k = 0; k < NWl; k++) c += __popcll(base[q * NWl + k]);
-			if (Y < Rl) c += (uint32_t)(base[G::xpl_off(l) + Z * NWl + (Y >> 6)] >> (Y & 63)) & 1u;
+			if (Y < Rl) c += (uint32_t)(base[xpl_off_rt<RB>(l) + Z * NWl + (Y >> 6)] >> (Y & 63)) & 1u;
 		} else {
 			const int Y = q - n_main;
-			for (int k = 0; k < NWl; k++) c += __popcll(base[G::zpl_off(l) + Y * NWl + k]);    // zero unless top
+			for (int k = 0; k < NWl; k++) c += __popcll(base[zpl_off_rt<RB>(l) + Y * NWl + k]);    // zero unless top
 		}
 		rowpre[r] = c;
 	}
@@ -439,58 +462,51 @@ k_splat(const VpWorldDev w, const uint32_t *__restrict__ ids, VpResultDev *__res
 
 	Ctx<RB> cx_{w, lv, own, nbx_xlo, nby, nbz, z0, (uint32_t)cx << RB, (uint32_t)cy << RB, (uint32_t)cz << RB};
 
-	// ---- phase 6a: level 0, one warp per non-empty row, lanes over the bits (coalesced 8 B stores) ----
+	// ---- phase 6: emission.  (a) every row expands its set bits into a shared list of (row, x) entries at
+	// the row's prefix position -- a short sequential loop per thread; (b) one thread per entry does the
+	// expensive part (colour gather, shadow sample, 8-byte store) with all lanes busy and fully coalesced
+	// stores.  The list is bounded (LIST_CAP), large chunks are emitted in several rounds. -------------
 	{
-		const int n_main = ZS * (R + 1), n_rows = n_main + (top ? R : 0);
-		unsigned long long *o0 = out + misc->base[0];
-		for (int r0 = warp * 32; r0 < n_rows; r0 += (kThreads / 32) * 32) {
-			const int r = r0 + lane;
-			const bool has = r < n_rows && rowpre[r + 1] != rowpre[r];
-			uint32_t todo = __ballot_sync(0xffffffffu, has);
-			while (todo) {
-				const int rr = r0 + __ffs(todo) - 1;
-				todo &= todo - 1;
-				uint32_t pos = rowpre[rr];               // row_off(0) == 0
-				int kind, Y, Zloc, Zc;
-				const uint64_t *bits;
-				if (rr < n_main) { Zloc = rr / (R + 1); Y = rr % (R + 1); Zc = z0 + Zloc; kind = Y < R ? MAIN : YPL; bits = lv0 + rr * NW; }
-				else { Y = rr - n_main; Zloc = 0; Zc = R; kind = ZPL; bits = lv0 + G::zpl_off(0) + Y * NW; }
-				const int Yc = kind == YPL ? R : Y;
-				#pragma unroll
-				for (int k = 0; k < NW; k++) {
-					const uint64_t wd = bits[k];
-					#pragma unroll
-					for (int h = 0; h < 2; h++) {
-						const int bit = h * 32 + lane;
-						if (bit < R && ((wd >> bit) & 1ull))
-							cx_.emit(o0 + pos + __popcll(wd & ((1ull << bit) - 1ull)), kind, 0, k * 64 + bit, Yc, Zloc, Zc);
-					}
-					pos += __popcll(wd);
-				}
-				if (kind == MAIN && lane == 0 && ((lv0[G::xpl_off(0) + Zloc * NW + (Y >> 6)] >> (Y & 63)) & 1ull))
-					cx_.emit(o0 + pos, XPL, 0, R, Y, Zloc, Zc);
-			}
-		}
-	}
-	// ---- phase 6b: levels 1..4, one thread per row (rows are short and few) -------------------------
-	for (int r = G::row_off(1) + tid; r < G::TR; r += kThreads) {
-		if (rowpre[r + 1] == rowpre[r]) continue;
-		int l = 1;
+		uint32_t *list = reinterpret_cast<uint32_t *>(smem + G::OFF_LIST);
+		const uint32_t T = rowpre[G::TR];
+		uint32_t lbase[5];
 		#pragma unroll
-		for (int k = 2; k < 5; k++) if (r >= G::row_off(k)) l = k;
-		const int q = r - G::row_off(l), Rl = G::Rl(l), n_main = G::Zl(l) * (Rl + 1);
-		unsigned long long *ol = out + misc->base[l] + (rowpre[r] - rowpre[G::row_off(l)]);
-		const uint64_t *base = lv + G::lvl_off(l);
-		if (q < n_main) {
-			const int Zloc = q / (Rl + 1), Y = q % (Rl + 1), Zc = (z0 >> l) + Zloc;
-			uint64_t wd = base[q];
-			const int kind = Y < Rl ? MAIN : YPL;
-			while (wd) { const int X = __ffsll((long long)wd) - 1; wd &= wd - 1; cx_.emit(ol++, kind, l, X, Y, Zloc, Zc); }
-			if (Y < Rl && ((base[G::xpl_off(l) + Zloc] >> Y) & 1ull)) cx_.emit(ol, XPL, l, Rl, Y, Zloc, Zc);
-		} else {
-			const int Y = q - n_main;
-			uint64_t wd = base[G::zpl_off(l) + Y];
-			while (wd) { const int X = __ffsll((long long)wd) - 1; wd &= wd - 1; cx_.emit(ol++, ZPL, l, X, Y, 0, Rl); }
+		for (int l = 0; l < 5; l++) lbase[l] = rowpre[G::row_off(l)];
+		for (uint32_t lo = 0; lo < T; lo += G::LIST_CAP) {
+			const uint32_t hi = min(lo + (uint32_t)G::LIST_CAP, T);
+			for (int r = tid; r < G::TR; r += kThreads) {
+				uint32_t p = rowpre[r];
+				const uint32_t e = rowpre[r + 1];
+				if (p == e || e <= lo || p >= hi) continue;
+				int l = 0;
+				#pragma unroll
+				for (int k = 1; k < 5; k++) if (r >= G::row_off(k)) l = k;
+				const int q = r - row_off_rt<RB>(l), Rl = R >> l, NWl = l == 0 ? NW : 1, n_main = (ZS >> l) * (Rl + 1);
+				const uint64_t *base = lv + lvl_off_rt<RB>(l);
+				const uint64_t *words = q < n_main ? base + q * NWl : base + zpl_off_rt<RB>(l) + (q - n_main) * NWl;
+				const uint32_t tag = (uint32_t)r << 8;
+				for (int k = 0; k < NWl; k++) {
+					uint64_t wd = words[k];
+					while (wd) {
+						const int x = __ffsll((long long)wd) - 1 + 64 * k;
+						wd &= wd - 1;
+						if (p >= lo && p < hi) list[p - lo] = tag | (uint32_t)x;
+						p++;
+					}
+				}
+				if (p < e && p >= lo && p < hi) list[p - lo] = tag | (uint32_t)Rl;      // the +x plane cell closes the row
+			}
+			__syncthreads();
+			for (uint32_t j = lo + tid; j < hi; j += kThreads) {
+				const uint32_t ent = list[j - lo];
+				const int r = (int)(ent >> 8), x = (int)(ent & 255u);
+				if (r < G::row_off(1)) cx_.template emit_entry<0>(out + misc->base[0] + (j - lbase[0]), r, x);
+				else if (r < G::row_off(2)) cx_.template emit_entry<1>(out + misc->base[1] + (j - lbase[1]), r - G::row_off(1), x);
+				else if (r < G::row_off(3)) cx_.template emit_entry<2>(out + misc->base[2] + (j - lbase[2]), r - G::row_off(2), x);
+				else if (r < G::row_off(4)) cx_.template emit_entry<3>(out + misc->base[3] + (j - lbase[3]), r - G::row_off(3), x);
+				else cx_.template emit_entry<4>(out + misc->base[4] + (j - lbase[4]), r - G::row_off(4), x);
+			}
+			__syncthreads();
 		}
 	}
 }
