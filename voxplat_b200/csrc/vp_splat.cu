@@ -19,6 +19,7 @@
 //      two uint16 loads.
 #include "vp_device.cuh"
 #include <cooperative_groups.h>
+#include <cstddef>
 namespace cg = cooperative_groups;
 using namespace vp;
 
@@ -54,10 +55,13 @@ template <int RB> struct Geo {
 	__host__ __device__ static constexpr int nrows(int l) { return Zl(l) * (Rl(l) + 1) + Rl(l); }
 	__host__ __device__ static constexpr int row_off(int l) { return l == 0 ? 0 : row_off(l - 1) + nrows(l - 1); }
 	static constexpr int TR = row_off(5);
+	// groups of 32 units (64-bit words) per level for counting / emission
+	__host__ __device__ static constexpr int ngroups(int l) { return (nrows(l) * NWl(l) + 31) / 32; }
+	__host__ __device__ static constexpr int grp_off(int l) { return l == 0 ? 0 : grp_off(l - 1) + ngroups(l - 1); }
+	static constexpr int NG = grp_off(5);
 	// shared memory carve-up (bytes)
 	static constexpr int RING_BYTES = kRing * TILE;
-	static constexpr int ROW_BYTES = (TR + 1) * 4;
-	static constexpr int SCRATCH0 = ((RING_BYTES > ROW_BYTES ? RING_BYTES : ROW_BYTES) + 127) / 128 * 128;   // ring, later the row prefix
+	static constexpr int SCRATCH0 = (RING_BYTES + 127) / 128 * 128;
 	static constexpr int HALO_BYTES = 2 * ZS * R;
 	static constexpr int OCC_WORDS = NSL * (R + 1) * NW;
 	static constexpr int OCCX_WORDS = ZS * NW;
@@ -67,10 +71,7 @@ template <int RB> struct Geo {
 	static constexpr int OFF_LV = OFF_OCCX + OCCX_WORDS * 8;
 	static constexpr int OFF_BARS = OFF_LV + LV_WORDS * 8;
 	static constexpr int OFF_MISC = OFF_BARS + (2 * kRing + 1) * 8;
-	static constexpr int SMEM = OFF_MISC + 256;
-	// entry list of phase 6: everything between the row prefix and the level bit arrays is dead by then
-	static constexpr int OFF_LIST = (ROW_BYTES + 15) / 16 * 16;
-	static constexpr int LIST_CAP = (OFF_LV - OFF_LIST) / 4;
+	static constexpr int SMEM = OFF_MISC + 128 + (NG + 1) * 4;
 };
 
 struct Misc {                       // small per-CTA scalars in shared memory
@@ -79,15 +80,12 @@ struct Misc {                       // small per-CTA scalars in shared memory
 	uint32_t base[5];               // first splat of this CTA's part of level l, relative to the chunk buffer
 	uint32_t total;                 // splats of the whole chunk
 	unsigned long long chunk_off;   // byte offset of the chunk buffer in the arena (~0 = not reserved)
+	uint32_t pad_[2];
+	uint32_t gpre[1];               // [NG + 1] exclusive prefix of the per-group splat counts (extends past the struct)
 };
+static_assert(offsetof(Misc, gpre) <= 128, "Misc header must fit the reserved 128 bytes");
 
 enum CellKind { MAIN = 0, XPL = 1, YPL = 2, ZPL = 3 };
-
-// runtime-level versions of the constexpr offset functions (select chains over compile-time constants)
-template <int RB> __device__ __forceinline__ int lvl_off_rt(int l) { using G = Geo<RB>; return l == 0 ? 0 : l == 1 ? G::lvl_off(1) : l == 2 ? G::lvl_off(2) : l == 3 ? G::lvl_off(3) : G::lvl_off(4); }
-template <int RB> __device__ __forceinline__ int row_off_rt(int l) { using G = Geo<RB>; return l == 0 ? 0 : l == 1 ? G::row_off(1) : l == 2 ? G::row_off(2) : l == 3 ? G::row_off(3) : G::row_off(4); }
-template <int RB> __device__ __forceinline__ int zpl_off_rt(int l) { using G = Geo<RB>; return l == 0 ? G::zpl_off(0) : l == 1 ? G::zpl_off(1) : l == 2 ? G::zpl_off(2) : l == 3 ? G::zpl_off(3) : G::zpl_off(4); }
-template <int RB> __device__ __forceinline__ int xpl_off_rt(int l) { using G = Geo<RB>; return l == 0 ? G::xpl_off(0) : l == 1 ? G::xpl_off(1) : l == 2 ? G::xpl_off(2) : l == 3 ? G::xpl_off(3) : G::xpl_off(4); }
 
 template <int RB> struct Ctx {
 	using G = Geo<RB>;
@@ -168,6 +166,65 @@ template <int RB> struct Ctx {
 	}
 };
 
+// Unit u of level L: its 64-bit word and the +x plane bit that follows it (0/1).
+template <int RB, int L>
+__device__ __forceinline__ uint64_t load_unit(const uint64_t *lv, int u, uint32_t &xb)
+{
+	using G = Geo<RB>;
+	constexpr int Rl = G::Rl(L), NWl = G::NWl(L), n_main = G::Zl(L) * (Rl + 1), U = G::nrows(L) * NWl;
+	xb = 0;
+	if (u >= U) return 0ull;
+	const uint64_t *base = lv + G::lvl_off(L);
+	if (u < n_main * NWl) {
+		if (u % NWl == NWl - 1) {
+			const int q = u / NWl, Z = q / (Rl + 1), Y = q - Z * (Rl + 1);
+			if (Y < Rl) xb = (uint32_t)(base[G::xpl_off(L) + Z * NWl + (Y >> 6)] >> (Y & 63)) & 1u;
+		}
+		return base[u];
+	}
+	return base[G::zpl_off(L) + (u - n_main * NWl)];
+}
+
+// position of the k-th (0-based) set bit of hi:lo; cl = popc(lo)
+__device__ __forceinline__ int select64(uint32_t lo, uint32_t hi, uint32_t cl, uint32_t k)
+{
+	uint32_t v = lo, c; int pos = 0;
+	if (k >= cl) { k -= cl; v = hi; pos = 32; }
+	c = __popc(v & 0xFFFFu); if (k >= c) { k -= c; v >>= 16; pos += 16; }
+	c = __popc(v & 0xFFu);   if (k >= c) { k -= c; v >>= 8;  pos += 8; }
+	c = __popc(v & 0xFu);    if (k >= c) { k -= c; v >>= 4;  pos += 4; }
+	c = __popc(v & 0x3u);    if (k >= c) { k -= c; v >>= 2;  pos += 2; }
+	c = v & 1u;              if (k >= c) { pos += 1; }
+	return pos;
+}
+
+template <int RB, int L>
+__device__ __forceinline__ void emit_group(const Ctx<RB> &cx, const uint64_t *lv, int gl, unsigned long long *out_g, int lane)
+{
+	using G = Geo<RB>;
+	constexpr int Rl = G::Rl(L), NWl = G::NWl(L);
+	uint32_t xb;
+	const uint64_t word = load_unit<RB, L>(lv, gl * 32 + lane, xb);
+	const uint32_t lo = (uint32_t)word, hi = (uint32_t)(word >> 32);
+	const uint32_t cl = __popc(lo), cw = cl + __popc(hi), c = cw + xb;
+	uint32_t inc = c;
+	#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
+	const uint32_t p = inc - c, S = __shfl_sync(0xffffffffu, inc, 31);
+	for (uint32_t s0 = 0; s0 < S; s0 += 32) {
+		const uint32_t s = min(s0 + (uint32_t)lane, S - 1);
+		int i = 0;
+		#pragma unroll
+		for (int d = 16; d >= 1; d >>= 1) { const uint32_t pj = __shfl_sync(0xffffffffu, p, i | d); if (pj <= s) i |= d; }
+		const uint32_t pi = __shfl_sync(0xffffffffu, p, i), wlo = __shfl_sync(0xffffffffu, lo, i), whi = __shfl_sync(0xffffffffu, hi, i);
+		const uint32_t wcl = __shfl_sync(0xffffffffu, cl, i), wcw = __shfl_sync(0xffffffffu, cw, i);
+		const uint32_t k = s - pi;
+		const int u = gl * 32 + i, q = u / NWl;
+		const int x = k == wcw ? Rl : select64(wlo, whi, wcl, k) + 64 * (u % NWl);
+		if (s0 + lane < S) cx.template emit_entry<L>(out_g + s0 + lane, q, x);
+	}
+}
+
 template <int RB>
 __global__ void __launch_bounds__(kThreads)
 k_splat(const VpWorldDev w, const uint32_t *__restrict__ ids, VpResultDev *__restrict__ results,
@@ -177,7 +234,6 @@ k_splat(const VpWorldDev w, const uint32_t *__restrict__ ids, VpResultDev *__res
 	constexpr int R = G::R, ZS = G::ZS, CL = G::CL, NW = G::NW, TILE = G::TILE, TPS = G::TPS, NT = G::NT;
 	extern __shared__ __align__(128) uint8_t smem[];
 	uint8_t *ring = smem;
-	uint32_t *rowpre = reinterpret_cast<uint32_t *>(smem);                 // aliases the ring after phase 1
 	uint8_t *halo = smem + G::OFF_HALO;
 	uint64_t *occ = reinterpret_cast<uint64_t *>(smem + G::OFF_OCC);
 	uint64_t *occx = reinterpret_cast<uint64_t *>(smem + G::OFF_OCCX);
@@ -376,41 +432,36 @@ k_splat(const VpWorldDev w, const uint32_t *__restrict__ ids, VpResultDev *__res
 		__syncthreads();
 	}
 
-	// ---- phase 4: per-row counts (popc) and their exclusive prefix = stable (z,y,x) ranks -----------
-	for (int r = tid; r < G::TR; r += kThreads) {
-		int l = 0;
-		#pragma unroll
-		for (int k = 1; k < 5; k++) if (r >= G::row_off(k)) l = k;
-		const int q = r - row_off_rt<RB>(l), Rl = R >> l, NWl = l == 0 ? NW : 1, n_main = (ZS >> l) * (Rl + 1);
-		const uint64_t *base = lv + lvl_off_rt<RB>(l);
-		uint32_t c = 0;
-		if (q < n_main) {
-			const int Z = q / (Rl + 1), Y = q % (Rl + 1);
-			for (int k = 0; k < NWl; k++) c += __popcll(base[q * NWl + k]);
-			if (Y < Rl) c += (uint32_t)(base[xpl_off_rt<RB>(l) + Z * NWl + (Y >> 6)] >> (Y & 63)) & 1u;
-		} else {
-			const int Y = q - n_main;
-			for (int k = 0; k < NWl; k++) c += __popcll(base[zpl_off_rt<RB>(l) + Y * NWl + k]);    // zero unless top
-		}
-		rowpre[r] = c;
+	// ---- phase 4: counts.  The bit rows of all levels are cut into groups of 32 "units" (one 64-bit word
+	// plus, for the last word of a slab row, the +x plane bit that follows it in scan order).  One warp
+	// per group: popc + one REDUX gives the group's splat count; a single warp then scans the group
+	// counts.  Stable (z,y,x) order follows from the prefix, not from atomics. --------------------------
+	uint32_t *gpre = misc->gpre;
+	for (int g = warp; g < G::NG; g += kThreads / 32) {
+		uint32_t xb, c;
+		if (g < G::grp_off(1)) { c = __popcll(load_unit<RB, 0>(lv, g * 32 + lane, xb)) + xb; }
+		else if (g < G::grp_off(2)) { c = __popcll(load_unit<RB, 1>(lv, (g - G::grp_off(1)) * 32 + lane, xb)) + xb; }
+		else if (g < G::grp_off(3)) { c = __popcll(load_unit<RB, 2>(lv, (g - G::grp_off(2)) * 32 + lane, xb)) + xb; }
+		else if (g < G::grp_off(4)) { c = __popcll(load_unit<RB, 3>(lv, (g - G::grp_off(3)) * 32 + lane, xb)) + xb; }
+		else { c = __popcll(load_unit<RB, 4>(lv, (g - G::grp_off(4)) * 32 + lane, xb)) + xb; }
+		c = __reduce_add_sync(0xffffffffu, c);
+		if (lane == 0) gpre[g] = c;
 	}
 	__syncthreads();
-	{
-		constexpr int IPT = (G::TR + kThreads - 1) / kThreads;
-		const int b0 = tid * IPT, b1 = min(b0 + IPT, G::TR);
-		uint32_t sum = 0;
-		for (int r = b0; r < b1; r++) sum += rowpre[r];
+	if (warp == 0) {
+		constexpr int IPT = (G::NG + 31) / 32;
+		uint32_t v[IPT], sum = 0;
+		#pragma unroll
+		for (int k = 0; k < IPT; k++) { const int g = lane * IPT + k; v[k] = g < G::NG ? gpre[g] : 0u; sum += v[k]; }
 		uint32_t inc = sum;
 		#pragma unroll
 		for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
-		if (lane == 31) misc->wsum[warp] = inc;
-		__syncthreads();
 		uint32_t pre = inc - sum;
-		for (int k = 0; k < warp; k++) pre += misc->wsum[k];
-		for (int r = b0; r < b1; r++) { uint32_t c = rowpre[r]; rowpre[r] = pre; pre += c; }
-		if (tid == kThreads - 1) rowpre[G::TR] = pre;
-		__syncthreads();
-		if (tid < 5) misc->cnt[tid] = rowpre[G::row_off(tid + 1)] - rowpre[G::row_off(tid)];      // row_off(5) == TR
+		#pragma unroll
+		for (int k = 0; k < IPT; k++) { const int g = lane * IPT + k; if (g < G::NG) gpre[g] = pre; pre += v[k]; }
+		if (lane == 31) gpre[G::NG] = pre;
+		__syncwarp();
+		if (lane < 5) misc->cnt[lane] = gpre[G::grp_off(lane + 1)] - gpre[G::grp_off(lane)];      // grp_off(5) == NG
 	}
 
 	// ---- phase 5: cluster exchange of the counts, one arena reservation per chunk -------------------
@@ -462,52 +513,19 @@ k_splat(const VpWorldDev w, const uint32_t *__restrict__ ids, VpResultDev *__res
 
 	Ctx<RB> cx_{w, lv, own, nbx_xlo, nby, nbz, z0, (uint32_t)cx << RB, (uint32_t)cy << RB, (uint32_t)cz << RB};
 
-	// ---- phase 6: emission.  (a) every row expands its set bits into a shared list of (row, x) entries at
-	// the row's prefix position -- a short sequential loop per thread; (b) one thread per entry does the
-	// expensive part (colour gather, shadow sample, 8-byte store) with all lanes busy and fully coalesced
-	// stores.  The list is bounded (LIST_CAP), large chunks are emitted in several rounds. -------------
-	{
-		uint32_t *list = reinterpret_cast<uint32_t *>(smem + G::OFF_LIST);
-		const uint32_t T = rowpre[G::TR];
-		uint32_t lbase[5];
-		#pragma unroll
-		for (int l = 0; l < 5; l++) lbase[l] = rowpre[G::row_off(l)];
-		for (uint32_t lo = 0; lo < T; lo += G::LIST_CAP) {
-			const uint32_t hi = min(lo + (uint32_t)G::LIST_CAP, T);
-			for (int r = tid; r < G::TR; r += kThreads) {
-				uint32_t p = rowpre[r];
-				const uint32_t e = rowpre[r + 1];
-				if (p == e || e <= lo || p >= hi) continue;
-				int l = 0;
-				#pragma unroll
-				for (int k = 1; k < 5; k++) if (r >= G::row_off(k)) l = k;
-				const int q = r - row_off_rt<RB>(l), Rl = R >> l, NWl = l == 0 ? NW : 1, n_main = (ZS >> l) * (Rl + 1);
-				const uint64_t *base = lv + lvl_off_rt<RB>(l);
-				const uint64_t *words = q < n_main ? base + q * NWl : base + zpl_off_rt<RB>(l) + (q - n_main) * NWl;
-				const uint32_t tag = (uint32_t)r << 8;
-				for (int k = 0; k < NWl; k++) {
-					uint64_t wd = words[k];
-					while (wd) {
-						const int x = __ffsll((long long)wd) - 1 + 64 * k;
-						wd &= wd - 1;
-						if (p >= lo && p < hi) list[p - lo] = tag | (uint32_t)x;
-						p++;
-					}
-				}
-				if (p < e && p >= lo && p < hi) list[p - lo] = tag | (uint32_t)Rl;      // the +x plane cell closes the row
-			}
-			__syncthreads();
-			for (uint32_t j = lo + tid; j < hi; j += kThreads) {
-				const uint32_t ent = list[j - lo];
-				const int r = (int)(ent >> 8), x = (int)(ent & 255u);
-				if (r < G::row_off(1)) cx_.template emit_entry<0>(out + misc->base[0] + (j - lbase[0]), r, x);
-				else if (r < G::row_off(2)) cx_.template emit_entry<1>(out + misc->base[1] + (j - lbase[1]), r - G::row_off(1), x);
-				else if (r < G::row_off(3)) cx_.template emit_entry<2>(out + misc->base[2] + (j - lbase[2]), r - G::row_off(2), x);
-				else if (r < G::row_off(4)) cx_.template emit_entry<3>(out + misc->base[3] + (j - lbase[3]), r - G::row_off(3), x);
-				else cx_.template emit_entry<4>(out + misc->base[4] + (j - lbase[4]), r - G::row_off(4), x);
-			}
-			__syncthreads();
-		}
+	// ---- phase 6: emission, one warp per group of 32 units.  Slot s of the group belongs to the unit i
+	// with p_i <= s < p_i + c_i (5-step binary search over the lanes' exclusive prefixes with shuffles),
+	// and inside the unit to its (s - p_i)-th set bit (branch-free popc select).  Every lane emits one
+	// splat per round, so the work is balanced whatever the distribution of visible voxels, and the
+	// 8-byte stores of a warp are contiguous. ---------------------------------------------------------------
+	for (int g = warp; g < G::NG; g += kThreads / 32) {
+		const uint32_t gs = gpre[g];
+		if (gpre[g + 1] == gs) continue;
+		if (g < G::grp_off(1)) emit_group<RB, 0>(cx_, lv, g, out + misc->base[0] + (gs - gpre[0]), lane);
+		else if (g < G::grp_off(2)) emit_group<RB, 1>(cx_, lv, g - G::grp_off(1), out + misc->base[1] + (gs - gpre[G::grp_off(1)]), lane);
+		else if (g < G::grp_off(3)) emit_group<RB, 2>(cx_, lv, g - G::grp_off(2), out + misc->base[2] + (gs - gpre[G::grp_off(2)]), lane);
+		else if (g < G::grp_off(4)) emit_group<RB, 3>(cx_, lv, g - G::grp_off(3), out + misc->base[3] + (gs - gpre[G::grp_off(3)]), lane);
+		else emit_group<RB, 4>(cx_, lv, g - G::grp_off(4), out + misc->base[4] + (gs - gpre[G::grp_off(4)]), lane);
 	}
 }
 
