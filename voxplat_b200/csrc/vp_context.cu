@@ -375,7 +375,18 @@ extern "C" int vp_batch_prepare(vp_ctx *c, const uint32_t *ids, uint32_t n, cons
 		if (ids[i] >= per_row * (uint32_t)c->nz || (int)cz < c->cfg.slab_z0 || (int)cz >= c->cfg.slab_z1)
 			return vp_fail(c, VP_ERR_NOT_RESIDENT, "vp_batch_prepare: chunk id outside the owned slab");
 		uint32_t f = per_chunk_flags ? per_chunk_flags[i] : flags;
-		if (f & VP_REBUILD_SPLAT) { sid.push_back(ids[i]); spos.push_back(i); }
+		if (f & VP_REBUILD_SPLAT) {
+			// mesher.c:404-409: a null chunk whose +x,+y,+z neighbours are null too has nothing visible; its
+			// (zeroed) result record is final, so it is not launched at all
+			const uint32_t cx = ids[i] % (uint32_t)c->nx, cy = (ids[i] / (uint32_t)c->nx) % (uint32_t)c->ny;
+			auto slot_of = [&](uint32_t x, uint32_t y, uint32_t z) -> int32_t {
+				if (x >= (uint32_t)c->nx || y >= (uint32_t)c->ny || z >= (uint32_t)c->nz || (int)z < c->ez0 || (int)z >= c->ez1) return -1;
+				return c->h_slot[(size_t)(z - (uint32_t)c->ez0) * per_row + (size_t)y * c->nx + x];
+			};
+			if (slot_of(cx, cy, cz) >= 0 || slot_of(cx + 1, cy, cz) >= 0 || slot_of(cx, cy + 1, cz) >= 0 || slot_of(cx, cy, cz + 1) >= 0) {
+				sid.push_back(ids[i]); spos.push_back(i);
+			}
+		}
 		if (f & VP_REBUILD_MESH) { mid.push_back(ids[i]); mpos.push_back(i); }
 	}
 	c->batch_n = n; c->n_splat = (uint32_t)sid.size(); c->n_mesh = (uint32_t)mid.size();

@@ -27,8 +27,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 {
 	uint32_t ok, a = smem_u32(bar);
 	do {
-		asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-		             : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+		asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+		             : "=r"(ok) : "r"(a), "r"(parity), "r"(2000u) : "memory");      // suspend up to ~2 us instead of spinning
 	} while (!ok);
 }
 // 1-D TMA bulk copy global -> shared, completion signalled on an mbarrier (bytes % 16 == 0, 16 B aligned).

@@ -27,7 +27,7 @@ namespace {
 
 constexpr int kConsumerWarps = 8;
 constexpr int kThreads = (kConsumerWarps + 1) * 32;     // + 1 producer warp
-constexpr int kRing = 8;                                // tiles in the TMA ring
+constexpr int kRing = 4;                                // tiles in the TMA ring
 
 template <int RB> struct Geo {
 	static constexpr int R = 1 << RB;
@@ -226,7 +226,7 @@ __device__ __forceinline__ void emit_group(const Ctx<RB> &cx, const uint64_t *lv
 }
 
 template <int RB>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, RB <= 6 ? 5 : 1)
 k_splat(const VpWorldDev w, const uint32_t *__restrict__ ids, VpResultDev *__restrict__ results,
         const uint32_t *__restrict__ result_pos, uint8_t *__restrict__ arena, VpArenaDev *__restrict__ st)
 {
@@ -272,11 +272,11 @@ k_splat(const VpWorldDev w, const uint32_t *__restrict__ ids, VpResultDev *__res
 
 	// ---- phase 0: barriers, zero the bit arrays ---------------------------------------------------
 	if (tid == 0) {
-		for (int i = 0; i < kRing; i++) { mbar_init(bar_full + i, 1); mbar_init(bar_empty + i, 1); }
+		for (int i = 0; i < kRing; i++) { mbar_init(bar_full + i, 1); mbar_init(bar_empty + i, kConsumerWarps / kRing); }
 		mbar_init(bar_halo, 1);
 		mbar_fence_init();
 	}
-	for (int i = tid; i < G::OCC_WORDS + G::OCCX_WORDS + G::LV_WORDS; i += kThreads) occ[i] = 0;   // occ, occx, lv are contiguous
+	for (int i = tid; i < G::OCC_WORDS + G::OCCX_WORDS; i += kThreads) occ[i] = 0;      // occ, occx are contiguous
 	__syncthreads();
 
 	// source of streamed slice s (z = z0 - 1 + s); nullptr = air or not needed
@@ -289,6 +289,7 @@ k_splat(const VpWorldDev w, const uint32_t *__restrict__ ids, VpResultDev *__res
 	const bool have_halo = nbx_xlo || nby;
 
 	// ---- phase 1: TMA producer (warp 8) / byte->bit consumers (warps 0..7) -------------------------
+	uint32_t any_solid = 0;
 	if (warp == kConsumerWarps) {
 		if (lane == 0) {
 			if (have_halo) {
@@ -309,15 +310,24 @@ k_splat(const VpWorldDev w, const uint32_t *__restrict__ ids, VpResultDev *__res
 			}
 		}
 	} else {
-		for (int t = warp; t < NT; t += kConsumerWarps) {
-			const int b = t % kRing, u = t / kRing, s = t / TPS, part = t % TPS;
+		// Each ring slot is drained by a FIXED pair of warps (half a tile each), so a warp meets the phases of
+		// its slot strictly in order -- with more consumers than slots a warp could otherwise run two phases
+		// ahead and alias the mbarrier parity.
+		constexpr int WPS = kConsumerWarps / kRing, PART = TILE / WPS;
+		const int b = warp % kRing, hpart = warp / kRing;
+		for (int t = b; t < NT; t += kRing) {
+			const int u = t / kRing, s = t / TPS, part = t % TPS;
 			mbar_wait(bar_full + b, u & 1);
 			if (slice_src(s)) {
 				const uint8_t *tb = ring + b * TILE;
 				uint64_t *orow = occ + (size_t)(s * (R + 1) + part * G::RPT) * NW;
 				#pragma unroll 4
-				for (int off = lane * 16; off < TILE; off += 512) {
-					uint32_t m = nz16(*reinterpret_cast<const uint4 *>(tb + off));
+				for (int off = hpart * PART + lane * 16; off < (hpart + 1) * PART; off += 512) {
+					const uint4 q4 = *reinterpret_cast<const uint4 *>(tb + off);
+					// all-air shortcut: the occupancy rows are pre-zeroed, so a warp that sees only zeros has nothing to do
+					if (PART >= 512 && !__any_sync(0xffffffffu, (q4.x | q4.y | q4.z | q4.w) != 0u)) continue;
+					const uint32_t m = nz16(q4);
+					any_solid |= m;
 					const int row = off / R, bo = off % R;
 					if (R >= 32) {
 						uint32_t v = m << (bo & 16);
@@ -339,6 +349,7 @@ k_splat(const VpWorldDev w, const uint32_t *__restrict__ ids, VpResultDev *__res
 				const bool isx = hr < ZS;
 				if (isx ? (nbx_xlo != nullptr) : (nby != nullptr)) {
 					uint32_t m = nz16(*reinterpret_cast<const uint4 *>(halo + hr * R + bo));
+					any_solid |= m;
 					uint64_t *dst = isx ? occx + hr * NW : occ + (size_t)((hr - ZS + 1) * (R + 1) + R) * NW;
 					if (R >= 32) {
 						uint32_t v = m << (bo & 16);
@@ -351,10 +362,17 @@ k_splat(const VpWorldDev w, const uint32_t *__restrict__ ids, VpResultDev *__res
 			}
 		}
 	}
+	// A slab without any solid voxel (own, slice above, +x/+y halo) has nothing visible: skip to the exchange.
+	const bool nonempty = __syncthreads_or(any_solid != 0u) != 0;
+	uint64_t *lv0 = lv;
+	uint32_t *gpre = misc->gpre;
+	if (!nonempty) {
+		if (tid < 5) misc->cnt[tid] = 0;
+	} else {
+	for (int i = tid; i < G::LV_WORDS; i += kThreads) lv[i] = 0;
 	__syncthreads();
 
 	// ---- phase 2: visibility rows (closed form of the pair walk, mesher.c:421-448) -------------------
-	uint64_t *lv0 = lv;
 	for (int f0 = warp * 32; f0 < ZS * R; f0 += (kThreads / 32) * 32) {
 		const int f = f0 + lane, zi = f >> RB, y = f & (R - 1), s = zi + 1;
 		const uint64_t *o = occ + (size_t)(s * (R + 1) + y) * NW;
@@ -436,7 +454,6 @@ k_splat(const VpWorldDev w, const uint32_t *__restrict__ ids, VpResultDev *__res
 	// plus, for the last word of a slab row, the +x plane bit that follows it in scan order).  One warp
 	// per group: popc + one REDUX gives the group's splat count; a single warp then scans the group
 	// counts.  Stable (z,y,x) order follows from the prefix, not from atomics. --------------------------
-	uint32_t *gpre = misc->gpre;
 	for (int g = warp; g < G::NG; g += kThreads / 32) {
 		uint32_t xb, c;
 		if (g < G::grp_off(1)) { c = __popcll(load_unit<RB, 0>(lv, g * 32 + lane, xb)) + xb; }
@@ -463,6 +480,7 @@ k_splat(const VpWorldDev w, const uint32_t *__restrict__ ids, VpResultDev *__res
 		__syncwarp();
 		if (lane < 5) misc->cnt[lane] = gpre[G::grp_off(lane + 1)] - gpre[G::grp_off(lane)];      // grp_off(5) == NG
 	}
+	}   // nonempty
 
 	// ---- phase 5: cluster exchange of the counts, one arena reservation per chunk -------------------
 	if (CL > 1) {
@@ -508,7 +526,7 @@ k_splat(const VpWorldDev w, const uint32_t *__restrict__ ids, VpResultDev *__res
 		}
 		__syncthreads();
 	}
-	if (misc->chunk_off == ~0ull || misc->total == 0) return;
+	if (!nonempty || misc->chunk_off == ~0ull || misc->total == 0) return;
 	unsigned long long *out = reinterpret_cast<unsigned long long *>(arena + misc->chunk_off);
 
 	Ctx<RB> cx_{w, lv, own, nbx_xlo, nby, nbz, z0, (uint32_t)cx << RB, (uint32_t)cy << RB, (uint32_t)cz << RB};
