@@ -100,7 +100,8 @@ k_rle_decode(const uint32_t *__restrict__ words, const unsigned long long *__res
 		const uint32_t adv = s_next[0];
 		wstart = s_next[1];
 		widx += adv;
-		if (covered >= N) break;
+		if (covered >= N || last) break;           // a short final tile: the tail below zero-fills and flags the stream
+		if (adv == 0) { if (tid == 0) atomicExch(status, 1u); break; }      // no progress (zero-length runs): malformed
 		__syncthreads();
 	}
 	// a short stream leaves the tail undefined in the reference; make it deterministic (zeros) and flag it
