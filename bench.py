@@ -1,0 +1,372 @@
+#!/usr/bin/env python
+"""bench.py -- Gvoxel/s culled+meshed of a full-world chunk rebuild (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+  python bench.py --impl reference --gpus N ...            # the reference's own CPU code on the host cores
+
+A step = one full rebuild of every chunk of the world: cull + 5 LOD splat lists for ALL chunks and the
+near-field quad mesh for the chunks within 512 voxels of the initial camera.
+N = 1: the default world 2048 x 256 x 2048 voxels, 64^3 chunks.  N > 1: weak scaling, the world grows
+along z to 2048 x 256 x (2048 N), one z-slab of 32 chunk rows per GPU, border planes exchanged with NCCL.
+Inputs are synthetic (voxplat_b200/csrc/vp_worldgen.c, seed 1234) and, at 1.07 GB per GPU, larger than L2.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SEED = 1234
+ROOT_BITW = 6
+BASE_BITS = (5, 2, 5)          # 2048 x 256 x 2048 voxels in 64^3 chunks
+
+
+def world_bits(n_gpus):
+    extra = int(np.log2(n_gpus))
+    assert (1 << extra) == n_gpus, "--gpus must be a power of two"
+    return (BASE_BITS[0], BASE_BITS[1], BASE_BITS[2] + extra)
+
+
+def workload_name(bits):
+    R = 1 << ROOT_BITW
+    return "%dx%dx%d voxels, chunk %d^3, full rebuild: splat(5 LOD) all chunks + mesh within 512 of camera" % (
+        (1 << bits[0]) * R, (1 << bits[1]) * R, (1 << bits[2]) * R, R)
+
+
+# ---------------------------------------------------------------------------------------------------
+# clocks: sample SM clock + throttle reasons DURING the timed region
+# ---------------------------------------------------------------------------------------------------
+class ClockSampler:
+    def __init__(self, device_index):
+        self.samples, self.reasons, self.stop_flag, self.thread = [], set(), False, None
+        self.max_mhz = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.005)
+
+    def start(self):
+        if self.nv:
+            self.thread = threading.Thread(target=self._loop, daemon=True)
+            self.thread.start()
+
+    def stop(self):
+        self.stop_flag = True
+        if self.thread:
+            self.thread.join()
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+# ---------------------------------------------------------------------------------------------------
+# host-side world pieces
+# ---------------------------------------------------------------------------------------------------
+def generate_slab(bits, z0, z1):
+    """Dense chunks of chunk rows [z0, min(z1+1, nz)) and the shadow rows the slab needs."""
+    from voxplat_b200 import worldgen
+    nx, ny, nz = (1 << b for b in bits)
+    per_row = nx * ny
+    R = 1 << ROOT_BITW
+    N = R ** 3
+    zg1 = min(z1 + 1, nz)                                   # one extra row: the shadow reach crosses the border
+    ids = np.arange(z0 * per_row, zg1 * per_row, dtype=np.uint32)
+    dense, solid = worldgen.gen_chunks(SEED, ROOT_BITW, bits, ids)
+    ptrs = [0] * (per_row * nz)
+    base = dense.ctypes.data
+    for k, cid in enumerate(ids):
+        if solid[k]:
+            ptrs[int(cid)] = base + k * N
+    sz0, sz1 = z0 * R, min(nz * R, z1 * R + 17)
+    rows = worldgen.shadow_rows(SEED, ROOT_BITW, bits, ptrs, sz0, sz1)
+    n_own = (z1 - z0) * per_row
+    return ids[:n_own], dense[:n_own], solid[:n_own], rows, sz0
+
+
+def algorithmic_bytes(own_ids, solid, res, bits):
+    """every input byte read once, every output byte written once."""
+    R = 1 << ROOT_BITW
+    nx, ny, nz = (1 << b for b in bits)
+    nn = solid > 0
+    splats = int(res["svl_items_total"].astype(np.int64).sum()) // 4
+    faces = int(res["vbo_items"].astype(np.int64).sum()) // 16
+    meshed = res["vbo_items"] > 0
+    # +x,+y,+z halo faces that exist inside the world (one R^2 plane each)
+    ids = own_ids.astype(np.int64)
+    cx, cy, cz = ids % nx, (ids // nx) % ny, ids // (nx * ny)
+    halo_planes = int(((cx + 1 < nx).astype(np.int64) + (cy + 1 < ny) + (cz + 1 < nz)).sum())
+    splat_bytes = int(nn.sum()) * R ** 3 + halo_planes * R * R + 12 * splats
+    mesh_bytes = int(meshed.sum()) * (R + 2) ** 3 + 64 * faces
+    return splat_bytes, mesh_bytes, splats, faces
+
+
+# ---------------------------------------------------------------------------------------------------
+# reference arm: the reference's own CPU implementation on the host cores
+# ---------------------------------------------------------------------------------------------------
+def reference_world(bits):
+    """The same seeded world inside the compiled reference (oracle/_ref) or, if that library did not
+    travel, inside the oracle port.  Returns (rebuild(ids, mode, threads) -> seconds, kind)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import helpers
+    from voxplat_b200 import worldgen
+    w = worldgen.World(SEED, ROOT_BITW, bits)
+    if helpers.ref_available():
+        rw = helpers.RefWorld(w)
+        return w, (lambda ids, mode, nt: rw.rebuild(ids, mode, nt)[0]), "reference"
+    ow = helpers.OracleWorld(w)
+    return w, (lambda ids, mode, nt: ow.rebuild(ids, mode, nt)[0]), "port"
+
+
+def cpu_rebuild_seconds(bits, sample_chunks=None):
+    """One full (or sampled) rebuild with every host thread: splat path on all sampled chunks + mesh path
+    on the near-camera ones.  Returns (seconds, voxels, cores, kind, sample description)."""
+    from voxplat_b200 import slab
+    w, rebuild, kind = reference_world(bits)
+    ids = np.arange(w.n_chunks, dtype=np.uint32)
+    if sample_chunks and sample_chunks < len(ids):
+        ids = ids[:sample_chunks]
+    near = ids[slab.near_camera_flags(ids, ROOT_BITW, bits)]
+    cores = os.cpu_count() or 1
+    t = rebuild(ids, 0, cores)
+    if len(near):
+        t += rebuild(near, 1, cores)
+    desc = "%d of %d chunks (%s), splat all + mesh %d near, %d threads, OpenMP dynamic" % (
+        len(ids), w.n_chunks, "whole world" if len(ids) == w.n_chunks else "first chunk rows", len(near), cores)
+    return t, len(ids) * w.N, cores, kind, desc
+
+
+def run_reference(args):
+    """Reference arm: build the world once, then time warmup + steps rebuilds of the bounded sample."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from voxplat_b200 import slab
+    bits = world_bits(args.gpus)
+    # bounded sample: one GPU's share of the workload = the N = 1 world (CPU throughput does not depend on the
+    # world's z extent), so the run ends within minutes and needs ~1 GB of host memory
+    sample_bits = world_bits(1)
+    w, rebuild, kind = reference_world(sample_bits)
+    n_sample = w.n_chunks
+    ids = np.arange(n_sample, dtype=np.uint32)
+    near = ids[slab.near_camera_flags(ids, ROOT_BITW, sample_bits)]
+    cores = os.cpu_count() or 1
+    times = []
+    for i in range(args.warmup + args.steps):
+        t = rebuild(ids, 0, cores) + (rebuild(near, 1, cores) if len(near) else 0.0)
+        if i >= args.warmup:
+            times.append(t)
+    sec = float(np.mean(times))
+    gv = n_sample * w.N / sec / 1e9
+    desc = "%d chunks per step = the 2048x256x2048 world (one GPU's share; splat all + mesh %d near), %d host threads, OpenMP dynamic schedule" % (
+        n_sample, len(near), cores)
+    line = {"impl": "reference", "metric": "Gvoxel/s culled+meshed (full-world chunk rebuild)", "value": gv, "unit": "Gvoxel/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic (seeded integer worldgen, seed 1234)",
+            "config": {"workload": workload_name(bits), "sample": desc},
+            "cpu_baseline": {"value": gv, "unit": "Gvoxel/s", "cores": cores, "kind": kind, "sample": desc},
+            "e2e": {"value": gv, "unit": "Gvoxel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------
+# native arm
+# ---------------------------------------------------------------------------------------------------
+def run_native(args):
+    import torch
+    import voxplat_b200 as vpb
+    from voxplat_b200 import slab
+
+    rank = int(os.environ.get("RANK", "0"))
+    world_size = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world_size == args.gpus, "launch with torchrun --nproc-per-node == --gpus"
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world_size > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    bits = world_bits(args.gpus)
+    nx, ny, nz = (1 << b for b in bits)
+    R, N = 1 << ROOT_BITW, 1 << (3 * ROOT_BITW)
+    z0, z1 = slab.slab_rows(nz, world_size, rank)
+    own_ids, dense, solid, shadow_rows, sz0 = generate_slab(bits, z0, z1)
+    nn = np.nonzero(solid)[0]
+
+    ctx = vpb.Context(ROOT_BITW, bits, device=local_rank, slab=(z0, z1), splat_arena_bytes=2 << 30, mesh_arena_bytes=2 << 30,
+                      rle_arena_bytes=1 << 30)
+    stream = torch.cuda.Stream()
+    ctx.set_stream(stream.cuda_stream)
+    pinned_dense = torch.from_numpy(np.ascontiguousarray(dense[nn])).pin_memory()
+    ctx.upload_chunks_dense(own_ids[nn], pinned_dense)
+    ctx.upload_shadow_rows(sz0, shadow_rows)
+
+    with torch.cuda.stream(stream):
+        rebuilder = slab.SlabRebuilder(ctx, rank, world_size, lambda n: torch.empty(n, dtype=torch.uint8, device="cuda"), dist=dist)
+        near = slab.near_camera_flags(own_ids, ROOT_BITW, bits)
+        flags = np.where(near, vpb.VP_REBUILD_SPLAT | vpb.VP_REBUILD_MESH, vpb.VP_REBUILD_SPLAT).astype(np.uint8)
+        ctx.batch_prepare(own_ids, per_chunk_flags=flags)
+
+        def step():
+            rebuilder.exchange_halos(mesh=True)
+            ctx.rebuild_device()
+
+        def barrier():
+            torch.cuda.synchronize()
+            if dist:
+                dist.barrier()
+            torch.cuda.synchronize()
+
+        for _ in range(max(args.warmup, 3)):
+            step()
+        barrier()
+        res, splat_bytes_out, mesh_bytes_out = ctx.rebuild_device_results()
+        launches0 = ctx.kernel_launches()
+        sampler = ClockSampler(local_rank)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sampler.start()
+        barrier()
+        ev0.record(stream)
+        for _ in range(args.steps):
+            step()
+        ev1.record(stream)
+        barrier()
+        clocks = sampler.stop()
+        ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device="cuda")
+        if dist:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        total_ms = float(ms.item())
+        launches = ctx.kernel_launches() - launches0
+        hist_n = min(args.steps, 256)
+        splat_ms, mesh_ms = ctx.kernel_ms_history(hist_n)
+
+        # ---- end to end through the host-facing C ABI: host RLE streams -> H2D -> decode -> rebuild -> D2H ----
+        words, offs = ctx.encode_chunks_rle(own_ids[nn])
+        pinned_words = torch.from_numpy(words).pin_memory()
+        pinned_shadow = torch.from_numpy(np.ascontiguousarray(shadow_rows)).pin_memory()
+        e2e_steps = max(3, min(args.steps, 10))
+
+        def e2e_step():
+            ctx.upload_chunks_rle(own_ids[nn], pinned_words, offs)          # rle_decompress of every chunk on the device
+            ctx.upload_shadow_rows(sz0, pinned_shadow)
+            rebuilder.exchange_halos(mesh=True)
+            r, sb, mb = ctx.rebuild_batch(own_ids, per_chunk_flags=flags)   # results land in pinned host staging
+            return r, sb, mb
+
+        for _ in range(3):
+            r_e, sb_e, mb_e = e2e_step()
+        barrier()
+        l0 = ctx.kernel_launches()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            r_e, sb_e, mb_e = e2e_step()
+        barrier()
+        e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        if dist:
+            dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+        e2e_launches = (ctx.kernel_launches() - l0) // e2e_steps
+        h2d = int(words.nbytes + offs.nbytes + pinned_shadow.numel() * 2 + own_ids[nn].nbytes + own_ids.nbytes + flags.nbytes)
+        d2h = int(sb_e.nbytes + mb_e.nbytes + r_e.nbytes)
+
+    # ---- reduce the per-rank figures ----
+    sb_a, mb_a, splats, faces = algorithmic_bytes(own_ids, solid, res, bits)
+    agg = torch.tensor([sb_a, mb_a, splats, faces, h2d, d2h, len(nn)], dtype=torch.float64, device="cuda")
+    if dist:
+        dist.all_reduce(agg)
+    total_vox = float(nx * ny * nz) * N
+    ms_per_step = total_ms / args.steps
+    value = total_vox / (ms_per_step * 1e-3) / 1e9
+    e2e_value = total_vox / (float(e2e_s.item()) / e2e_steps) / 1e9
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (of fallback)"
+        k_ms = float(np.mean(splat_ms))
+        achieved = sb_a / (k_ms * 1e-3) / 1e9
+        traffic = None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "splat_traffic.json")))
+            if tj.get("workload_bits") == list(bits):
+                traffic = tj["dram_bytes_per_launch"]
+        except Exception:
+            pass
+        line = {
+            "metric": "Gvoxel/s culled+meshed (full-world chunk rebuild)", "value": value, "unit": "Gvoxel/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+            "data": "synthetic (seeded integer worldgen, seed 1234)",
+            "config": {"workload": workload_name(bits), "chunks": int(nx * ny * nz), "non_null_chunks": int(agg[6].item()),
+                       "parallelism": "z-slabs of %d chunk rows per GPU, NCCL border planes" % (nz // world_size) if world_size > 1 else "single GPU",
+                       "l2": "inputs larger than L2 (%.2f GB of voxels per GPU, no flush needed)" % (len(nn) * N / 1e9),
+                       "splats": int(agg[2].item()), "mesh_faces": int(agg[3].item())},
+            "roofline": {"bound": "hbm", "kernel": "k_splat (cull + 5 LOD + splat emission), rank 0", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": sb_a, "kernel_ms": k_ms,
+                         "mesh_kernel": {"kernel_ms": float(np.mean(mesh_ms)), "algorithmic_bytes_per_launch": mb_a,
+                                         "achieved": mb_a / max(float(np.mean(mesh_ms)), 1e-9) / 1e6}},
+            "e2e": {"value": e2e_value, "unit": "Gvoxel/s", "h2d_bytes_per_step": int(agg[4].item()), "d2h_bytes_per_step": int(agg[5].item()),
+                    "ms_per_step": float(e2e_s.item()) / e2e_steps * 1e3, "steps": e2e_steps,
+                    "path": "host RLE streams (pinned) -> vp_upload_chunks_rle (H2D + device decode) -> vp_rebuild_batch -> pinned host staging",
+                    "gpu_launches_per_step": int(e2e_launches)},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+        }
+        if args.gpus == 1 and not args.no_cpu_baseline:
+            t, vox, cores, kind, desc = cpu_rebuild_seconds(bits)
+            line["cpu_baseline"] = {"value": vox / t / 1e9, "unit": "Gvoxel/s", "cores": cores, "kind": kind, "sample": desc,
+                                    "seconds": t}
+        print(json.dumps(line))
+    ctx.close()
+    if dist:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_native(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -158,6 +158,10 @@ VP_API int  vp_batch_prepare(vp_ctx *ctx, const uint32_t *chunk_ids, uint32_t n,
                       uint32_t flags);
 VP_API int  vp_rebuild_device(vp_ctx *ctx);
 VP_API int  vp_rebuild_device_results(vp_ctx *ctx, vp_chunk_result *results, uint64_t *splat_bytes, uint64_t *mesh_bytes);
+/* Device time of the kernels of the last n (<= 256) vp_rebuild_device calls, oldest first (CUDA events on the
+ * context stream): splat_ms[k] = cull+LOD+splat kernel, mesh_ms[k] = mesh kernel (0 if not launched).
+ * Synchronises the stream. */
+VP_API int  vp_kernel_ms_history(vp_ctx *ctx, uint32_t n, float *splat_ms, float *mesh_ms);
 /* Device pointers of the arenas (for zero-copy consumers / tests). */
 VP_API void *vp_splat_arena_device(vp_ctx *ctx);
 VP_API void *vp_mesh_arena_device(vp_ctx *ctx);

@@ -72,6 +72,7 @@ def load_library():
         "vp_batch_prepare": (C.c_int, [vp, vp, C.c_uint32, vp, C.c_uint32]),
         "vp_rebuild_device": (C.c_int, [vp]),
         "vp_rebuild_device_results": (C.c_int, [vp, vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+        "vp_kernel_ms_history": (C.c_int, [vp, C.c_uint32, vp, vp]),
         "vp_splat_arena_device": (vp, [vp]),
         "vp_mesh_arena_device": (vp, [vp]),
         "vp_arena_download": (C.c_int, [vp, C.c_int, vp, C.c_uint64]),
@@ -235,6 +236,12 @@ class Context:
         sb, mb = C.c_uint64(), C.c_uint64()
         self._ck(self.lib.vp_rebuild_device_results(self.h, _ptr(res), C.byref(sb), C.byref(mb)))
         return res, sb.value, mb.value
+
+    def kernel_ms_history(self, n):
+        """(splat_ms[n], mesh_ms[n]) of the last n rebuild_device calls."""
+        a, b = np.zeros(n, np.float32), np.zeros(n, np.float32)
+        self._ck(self.lib.vp_kernel_ms_history(self.h, n, _ptr(a), _ptr(b)))
+        return a, b
 
     def arena_download(self, which, nbytes):
         out = np.empty(nbytes, np.uint8)

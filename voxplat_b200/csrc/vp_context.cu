@@ -107,6 +107,7 @@ static void ctx_free(vp_ctx *c)
 	if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
 	if (c->ev_a) cudaEventDestroy(c->ev_a);
 	if (c->ev_b) cudaEventDestroy(c->ev_b);
+	for (int h = 0; h < vp_ctx::kHist; h++) for (int i = 0; i < 4; i++) if (c->ev_k[h][i]) cudaEventDestroy(c->ev_k[h][i]);
 	delete c;
 }
 
@@ -146,6 +147,7 @@ extern "C" int vp_ctx_create(const vp_config *cfg, vp_ctx **out)
 	CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
 	CK(cudaEventCreateWithFlags(&c->ev_a, cudaEventDisableTiming));
 	CK(cudaEventCreateWithFlags(&c->ev_b, cudaEventDisableTiming));
+	for (int h = 0; h < vp_ctx::kHist; h++) for (int i = 0; i < 4; i++) CK(cudaEventCreate(&c->ev_k[h][i]));
 	c->stream = c->own_stream;
 	CK(cudaMalloc(&c->vox_pool, (size_t)c->n_slots * N));
 	CK(cudaMalloc(&c->xlo_pool, (size_t)c->n_slots * RR));
@@ -414,12 +416,22 @@ extern "C" int vp_rebuild_device(vp_ctx *c)
 	VP_CUDA(c, cudaMemcpyAsync(c->d_arena_state, c->h_arena_state + 3, 2 * sizeof(VpArenaDev), cudaMemcpyHostToDevice, c->stream));
 	VP_CUDA(c, cudaMemsetAsync(c->d_results, 0, (size_t)c->batch_n * sizeof(VpResultDev), c->stream));
 	VpWorldDev w = vp_world_dev(c);
+	cudaEvent_t *ev = c->ev_k[c->rebuilds % vp_ctx::kHist];
+	uint8_t &valid = c->ev_k_valid[c->rebuilds % vp_ctx::kHist];
+	valid = 0;
+	c->rebuilds++;
 	if (c->n_splat) {
+		VP_CUDA(c, cudaEventRecord(ev[0], c->stream));
 		VP_CUDA(c, vp_launch_splat(w, c->d_splat_ids, c->n_splat, c->d_results, c->d_splat_pos, c->d_splat_arena, c->d_arena_state + 0, c->stream));
+		VP_CUDA(c, cudaEventRecord(ev[1], c->stream));
+		valid |= 1;
 		c->launches++;
 	}
 	if (c->n_mesh) {
+		VP_CUDA(c, cudaEventRecord(ev[2], c->stream));
 		VP_CUDA(c, vp_launch_mesh(w, c->d_mesh_ids, c->n_mesh, c->d_results, c->d_mesh_pos, c->d_mesh_arena, c->d_arena_state + 1, c->stream));
+		VP_CUDA(c, cudaEventRecord(ev[3], c->stream));
+		valid |= 2;
 		c->launches++;
 	}
 	return VP_OK;
@@ -437,6 +449,24 @@ extern "C" int vp_rebuild_device_results(vp_ctx *c, vp_chunk_result *results, ui
 	if (mesh_bytes) *mesh_bytes = c->h_arena_state[1].cursor;
 	if (c->h_arena_state[0].overflow || c->h_arena_state[1].overflow)
 		return vp_fail(c, VP_ERR_ARENA_FULL, "output arena too small (cursor values give the required bytes)");
+	return VP_OK;
+}
+
+extern "C" int vp_kernel_ms_history(vp_ctx *c, uint32_t n, float *splat_ms, float *mesh_ms)
+{
+	if (!c || n > (uint32_t)vp_ctx::kHist || n > c->rebuilds) return vp_fail(c, VP_ERR_ARG, "vp_kernel_ms_history: n exceeds the recorded history");
+	VP_CUDA(c, cudaSetDevice(c->cfg.device));
+	VP_CUDA(c, cudaStreamSynchronize(c->stream));
+	for (uint32_t k = 0; k < n; k++) {
+		const uint64_t step = c->rebuilds - n + k;
+		cudaEvent_t *ev = c->ev_k[step % vp_ctx::kHist];
+		const uint8_t valid = c->ev_k_valid[step % vp_ctx::kHist];
+		float a = 0.0f, b = 0.0f;
+		if (valid & 1) VP_CUDA(c, cudaEventElapsedTime(&a, ev[0], ev[1]));
+		if (valid & 2) VP_CUDA(c, cudaEventElapsedTime(&b, ev[2], ev[3]));
+		if (splat_ms) splat_ms[k] = a;
+		if (mesh_ms) mesh_ms[k] = b;
+	}
 	return VP_OK;
 }
 

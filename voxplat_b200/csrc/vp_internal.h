@@ -57,6 +57,10 @@ struct vp_ctx {
 	cudaStream_t own_stream, stream;
 	cudaStream_t copy_stream;
 	cudaEvent_t ev_a, ev_b;
+	static constexpr int kHist = 256;
+	cudaEvent_t ev_k[kHist][4];   // timing events around the splat [0,1] and mesh [2,3] kernels of the last kHist rebuilds
+	uint8_t ev_k_valid[kHist];    // bit0 splat, bit1 mesh recorded
+	uint64_t rebuilds;            // vp_rebuild_device calls so far
 	// world
 	uint8_t *vox_pool, *xlo_pool, *xhi_pool;
 	uint32_t n_slots;             // capacity of the pools in chunks

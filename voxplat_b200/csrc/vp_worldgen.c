@@ -79,13 +79,12 @@ static int32_t column_height(const vpw_params *P, uint32_t x, uint32_t z)
 	/* per-column jitter: 3*n(5x) + 2*n(10x) in the reference is effectively white noise in [-5,5] */
 	uint32_t j = hash3(P->seed, 6, x, z);
 	h += (int32_t)((j & 7) + ((j >> 3) & 3)) - 5 + (int32_t)((j >> 5) & 1);
-	/* edge fall-off: 5*min(1-|x-c|/c, 1-|z-c|/c) clamped to 1 (centre taken from the x size, as gen.c:128) */
-	int32_t c = (int32_t)(wx / 2);
+	/* edge fall-off over the outer fifth of the world (gen.c:128-135), measured to the nearest x / z edge */
+	int32_t c = (int32_t)(wx / 2), cz = (int32_t)(wz / 2);
 	int32_t dx = (int32_t)x - c; if (dx < 0) dx = -dx; if (dx > c) dx = c;
-	int32_t dz = (int32_t)z - c; if (dz < 0) dz = -dz; if (dz > c) dz = c;
-	int32_t ex = c - dx, ez = c - dz, e = ex < ez ? ex : ez;                /* in units of 1/c */
+	int32_t dz = (int32_t)z - cz; if (dz < 0) dz = -dz; if (dz > cz) dz = cz;
+	int32_t ex = c - dx, ez = cz - dz, e = ex < ez ? ex : ez;               /* voxels to the nearest x / z edge */
 	if (5 * e < c) h = (int32_t)(((int64_t)h * 5 * e) / c);
-	(void)wz;
 	h -= 60;                                                                 /* water level */
 	if (h < 8) h = 8;
 	if (h > (int32_t)wy - 24) h = (int32_t)wy - 24;                          /* leave room for a tree */
