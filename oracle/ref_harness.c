@@ -299,6 +299,16 @@ VR_EXPORT double vr_world_rebuild(struct ChunkSet *set, const uint32_t *ids, uin
 
 /* ---- the reference's own dispatcher, for drop-in comparisons ---- */
 VR_EXPORT void vr_manage(struct ChunkSet *set) { chunkset_manage(set); }
+#ifdef VR_WITH_GPU
+/* libvoxref_gpu.so only: chunkset_manage is the CUDA drop-in, the reference's own loop is chunkset_manage_cpu */
+void chunkset_manage_cpu(struct ChunkSet *set);
+VR_EXPORT void vr_manage_cpu(struct ChunkSet *set) { chunkset_manage_cpu(set); }
+#endif
+VR_EXPORT int vr_chunk_pending(struct ChunkSet *set, uint32_t id)
+{
+	struct ChunkMD *c = &set->chunks[id];
+	return c->dirty | c->remesh | c->changing;
+}
 
 VR_EXPORT void vr_chunk_set_make_mesh(struct ChunkSet *set, uint32_t id, int v)
 {

@@ -551,6 +551,26 @@ extern "C" int vp_chunk_make_mesh(vp_ctx *c, uint32_t chunk_id, int16_t *geometr
 
 // ---- multi-GPU slab borders ---------------------------------------------------------------------------
 
+// Give every chunk of ghost row `row` a zero-filled slot (once).  Ghost chunks only ever hold the border slice.
+static int ghost_row_init(vp_ctx *c, int row)
+{
+	const uint32_t per_row = (uint32_t)c->nx * c->ny;
+	const size_t N = (size_t)1 << (3 * c->rb);
+	bool all = true;
+	for (uint32_t i = 0; i < per_row && all; i++) all = c->h_slot[(size_t)(row - c->ez0) * per_row + i] >= 0;
+	if (all) return VP_OK;
+	std::vector<uint32_t> ids(per_row);
+	std::vector<uint8_t> want(per_row, 1);
+	for (uint32_t i = 0; i < per_row; i++) ids[i] = (uint32_t)row * per_row + i;
+	std::vector<int32_t> slots;
+	int rc = assign_slots(c, ids.data(), per_row, want.data(), slots);
+	if (rc) return rc;
+	for (uint32_t i = 0; i < per_row; i++) VP_CUDA(c, cudaMemsetAsync(c->vox_pool + (size_t)slots[i] * N, 0, N, c->stream));
+	if ((rc = push_slot_table(c, ids.data(), per_row))) return rc;
+	VP_CUDA(c, cudaStreamSynchronize(c->stream));
+	return VP_OK;
+}
+
 extern "C" uint64_t vp_halo_plane_bytes(vp_ctx *c) { return c ? (uint64_t)c->nx * c->ny << (2 * c->rb) : 0; }
 
 extern "C" int vp_halo_pack(vp_ctx *c, int which, void *device_buf)
@@ -573,29 +593,15 @@ extern "C" int vp_halo_unpack(vp_ctx *c, int which, const void *device_buf)
 	const uint32_t per_row = (uint32_t)c->nx * c->ny;
 	const int row = which == 0 ? c->cfg.slab_z1 : c->cfg.slab_z0 - 1;
 	if (row < c->ez0 || row >= c->ez1) return vp_fail(c, VP_ERR_ARG, "vp_halo_unpack: no ghost row on that side");
-	const size_t N = (size_t)1 << (3 * c->rb);
-	// which ghost chunks have any solid voxel in the plane?
-	uint32_t *d_flags32 = reinterpret_cast<uint32_t *>(c->d_tmp_slots);
-	k_plane_nonzero<<<per_row, 256, 0, c->stream>>>(c->rb, (const uint8_t *)device_buf, d_flags32);
-	VP_CUDA(c, cudaGetLastError());
-	std::vector<uint32_t> flags(per_row);
-	VP_CUDA(c, cudaMemcpyAsync(flags.data(), d_flags32, (size_t)per_row * 4, cudaMemcpyDeviceToHost, c->stream));
-	VP_CUDA(c, cudaStreamSynchronize(c->stream));
-	std::vector<uint32_t> ids(per_row);
-	std::vector<uint8_t> want(per_row);
-	for (uint32_t i = 0; i < per_row; i++) { ids[i] = (uint32_t)row * per_row + i; want[i] = flags[i] != 0; }
-	std::vector<int32_t> slots;
-	int rc = assign_slots(c, ids.data(), per_row, want.data(), slots);
+	// Ghost rows own permanent, zero-filled slots (allocated on first use), so an exchange is two kernels and
+	// no host round trip: copy the plane into the border slice, refresh the x-face planes.
+	int rc = ghost_row_init(c, row);
 	if (rc) return rc;
-	for (uint32_t i = 0; i < per_row; i++)      // ghost chunks hold only the border slice; keep the rest deterministic
-		if (slots[i] >= 0) VP_CUDA(c, cudaMemsetAsync(c->vox_pool + (size_t)slots[i] * N, 0, N, c->stream));
-	if ((rc = push_slot_table(c, ids.data(), per_row))) return rc;
 	const int32_t *row_slots = c->d_slot + (size_t)(row - c->ez0) * per_row;
 	k_plane_copy<<<per_row, 256, 0, c->stream>>>(c->rb, c->vox_pool, row_slots, (uint8_t *)const_cast<void *>(device_buf), which == 0 ? 0 : c->R - 1, 1);
 	VP_CUDA(c, cudaGetLastError());
 	VP_CUDA(c, vp_launch_extract_xfaces(c->rb, c->vox_pool, c->xlo_pool, c->xhi_pool, row_slots, per_row, c->stream));
-	c->launches += 3;
-	VP_CUDA(c, cudaStreamSynchronize(c->stream));
+	c->launches += 2;
 	return VP_OK;
 }
 
