@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libvoxplat_b200.so")
+LIB_PATH = os.environ.get("VOXPLAT_B200_LIB", os.path.join(HERE, "libvoxplat_b200.so"))      # override: kernel tuning variants
 
 VP_REBUILD_SPLAT = 1
 VP_REBUILD_MESH = 2
