@@ -87,6 +87,17 @@ static_assert(offsetof(Misc, gpre) <= 128, "Misc header must fit the reserved 12
 
 enum CellKind { MAIN = 0, XPL = 1, YPL = 2, ZPL = 3 };
 
+// Optional phase timing (VP_NVCC_EXTRA=-DVP_PROFILE_PHASES, scripts/phase_probe.py): thread 0 of every CTA
+// accumulates clock64 deltas per phase.  Compiled out by default.
+#ifdef VP_PROFILE_PHASES
+__device__ unsigned long long g_phase_cycles[8];
+#define VP_PHASE(k) do { if (threadIdx.x == 0) { long long t__ = clock64(); atomicAdd(&g_phase_cycles[k], (unsigned long long)(t__ - t_prev__)); t_prev__ = t__; } } while (0)
+#define VP_PHASE_INIT long long t_prev__ = clock64()
+#else
+#define VP_PHASE(k) do { } while (0)
+#define VP_PHASE_INIT do { } while (0)
+#endif
+
 template <int RB> struct Ctx {
 	using G = Geo<RB>;
 	const VpWorldDev &w;
@@ -270,6 +281,7 @@ k_splat(const VpWorldDev w, const uint32_t *__restrict__ ids, VpResultDev *__res
 		return;                                        // uniform over the whole cluster
 	}
 
+	VP_PHASE_INIT;
 	// ---- phase 0: barriers, zero the bit arrays ---------------------------------------------------
 	if (tid == 0) {
 		for (int i = 0; i < kRing; i++) { mbar_init(bar_full + i, 1); mbar_init(bar_empty + i, kConsumerWarps / kRing); }
@@ -288,6 +300,7 @@ k_splat(const VpWorldDev w, const uint32_t *__restrict__ ids, VpResultDev *__res
 	};
 	const bool have_halo = nbx_xlo || nby;
 
+	VP_PHASE(0);
 	// ---- phase 1: TMA producer (warp 8) / byte->bit consumers (warps 0..7) -------------------------
 	uint32_t any_solid = 0;
 	if (warp == kConsumerWarps) {
@@ -369,6 +382,7 @@ k_splat(const VpWorldDev w, const uint32_t *__restrict__ ids, VpResultDev *__res
 	if (!nonempty) {
 		if (tid < 5) misc->cnt[tid] = 0;
 	} else {
+	VP_PHASE(1);
 	for (int i = tid; i < G::LV_WORDS; i += kThreads) lv[i] = 0;
 	__syncthreads();
 
@@ -407,6 +421,7 @@ k_splat(const VpWorldDev w, const uint32_t *__restrict__ ids, VpResultDev *__res
 	}
 	__syncthreads();
 
+	VP_PHASE(2);
 	// ---- phase 3: LOD pyramids, level l from l-1 by OR of the child rows + pair-OR-compress ---------
 	#pragma unroll
 	for (int l = 1; l < 5; l++) {
@@ -450,6 +465,7 @@ k_splat(const VpWorldDev w, const uint32_t *__restrict__ ids, VpResultDev *__res
 		__syncthreads();
 	}
 
+	VP_PHASE(3);
 	// ---- phase 4: counts.  The bit rows of all levels are cut into groups of 32 "units" (one 64-bit word
 	// plus, for the last word of a slab row, the +x plane bit that follows it in scan order).  One warp
 	// per group: popc + one REDUX gives the group's splat count; a single warp then scans the group
@@ -482,6 +498,7 @@ k_splat(const VpWorldDev w, const uint32_t *__restrict__ ids, VpResultDev *__res
 	}
 	}   // nonempty
 
+	VP_PHASE(4);
 	// ---- phase 5: cluster exchange of the counts, one arena reservation per chunk -------------------
 	if (CL > 1) {
 		cg::cluster_group cluster = cg::this_cluster();
@@ -526,6 +543,7 @@ k_splat(const VpWorldDev w, const uint32_t *__restrict__ ids, VpResultDev *__res
 		}
 		__syncthreads();
 	}
+	VP_PHASE(5);
 	if (!nonempty || misc->chunk_off == ~0ull || misc->total == 0) return;
 	unsigned long long *out = reinterpret_cast<unsigned long long *>(arena + misc->chunk_off);
 
@@ -545,6 +563,10 @@ k_splat(const VpWorldDev w, const uint32_t *__restrict__ ids, VpResultDev *__res
 		else if (g < G::grp_off(4)) emit_group<RB, 3>(cx_, lv, g - G::grp_off(3), out + misc->base[3] + (gs - gpre[G::grp_off(3)]), lane);
 		else emit_group<RB, 4>(cx_, lv, g - G::grp_off(4), out + misc->base[4] + (gs - gpre[G::grp_off(4)]), lane);
 	}
+#ifdef VP_PROFILE_PHASES
+	__syncthreads();
+	VP_PHASE(6);
+#endif
 }
 
 template <int RB>
@@ -591,3 +613,13 @@ int vp_splat_smem_bytes(int rb)
 	switch (rb) { case 4: return Geo<4>::SMEM; case 5: return Geo<5>::SMEM; case 6: return Geo<6>::SMEM; case 7: return Geo<7>::SMEM; }
 	return -1;
 }
+
+#ifdef VP_PROFILE_PHASES
+extern "C" __attribute__((visibility("default"))) int vp_debug_phase_cycles(unsigned long long out[8], int reset)
+{
+	cudaDeviceSynchronize();
+	cudaError_t e = cudaMemcpyFromSymbol(out, g_phase_cycles, sizeof(unsigned long long) * 8);
+	if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(g_phase_cycles, z, sizeof z); }
+	return (int)e;
+}
+#endif
