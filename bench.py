@@ -27,9 +27,19 @@ ROOT_BITW = 6
 BASE_BITS = (5, 2, 5)          # 2048 x 256 x 2048 voxels in 64^3 chunks
 
 
+WORKLOADS = {            # chunk-grid bit widths (64^3 chunks); c2 grows along z with the GPU count (weak scaling)
+    "c2": None,           # BASELINE config 2: 2048 x 256 x 2048 per GPU
+    "c3": (7, 3, 7),      # BASELINE config 3: 8192 x 512 x 8192, fixed world split over the GPUs (strong scaling)
+    "c4": (8, 3, 8),      # BASELINE config 4: 16384 x 512 x 16384 (the README's 128 GB map), 8 GPUs
+}
+WORKLOAD = "c2"
+
+
 def world_bits(n_gpus):
     extra = int(np.log2(n_gpus))
     assert (1 << extra) == n_gpus, "--gpus must be a power of two"
+    if WORKLOADS[WORKLOAD] is not None:
+        return WORKLOADS[WORKLOAD]
     return (BASE_BITS[0], BASE_BITS[1], BASE_BITS[2] + extra)
 
 
@@ -221,8 +231,9 @@ def run_native(args):
     own_ids, dense, solid, shadow_rows, sz0 = generate_slab(bits, z0, z1)
     nn = np.nonzero(solid)[0]
 
-    ctx = vpb.Context(ROOT_BITW, bits, device=local_rank, slab=(z0, z1), splat_arena_bytes=2 << 30, mesh_arena_bytes=2 << 30,
-                      rle_arena_bytes=1 << 30)
+    own_vox = len(own_ids) * N
+    ctx = vpb.Context(ROOT_BITW, bits, device=local_rank, slab=(z0, z1), splat_arena_bytes=max(2 << 30, own_vox // 2),
+                      mesh_arena_bytes=2 << 30, rle_arena_bytes=max(1 << 30, own_vox // 4))
     stream = torch.cuda.Stream()
     ctx.set_stream(stream.cuda_stream)
     pinned_dense = torch.from_numpy(np.ascontiguousarray(dense[nn])).pin_memory()
@@ -326,9 +337,9 @@ def run_native(args):
         line = {
             "metric": "Gvoxel/s culled+meshed (full-world chunk rebuild)", "value": value, "unit": "Gvoxel/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+            "higher_is_better": True, "scaling": "weak" if WORKLOAD == "c2" else "strong", "vs_baseline": None, "dtype": "u8",
             "data": "synthetic (seeded integer worldgen, seed 1234)",
-            "config": {"workload": workload_name(bits), "chunks": int(nx * ny * nz), "non_null_chunks": int(agg[6].item()),
+            "config": {"workload": workload_name(bits), "baseline_config": WORKLOAD, "chunks": int(nx * ny * nz), "non_null_chunks": int(agg[6].item()),
                        "parallelism": "z-slabs of %d chunk rows per GPU, NCCL border planes" % (nz // world_size) if world_size > 1 else "single GPU",
                        "l2": "inputs larger than L2 (%.2f GB of voxels per GPU, no flush needed)" % (len(nn) * N / 1e9),
                        "splats": int(agg[2].item()), "mesh_faces": int(agg[3].item())},
@@ -361,7 +372,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS), help="BASELINE.json config (default c2, the metric's config)")
     args = ap.parse_args()
+    global WORKLOAD
+    WORKLOAD = args.workload
     if args.impl == "reference":
         run_reference(args)
     else:
