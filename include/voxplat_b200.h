@@ -151,6 +151,14 @@ VP_API int  vp_rebuild_batch(vp_ctx *ctx, const uint32_t *chunk_ids, uint32_t n,
                       const uint8_t *per_chunk_flags, vp_chunk_result *results,
                       const void **splat_base, const void **mesh_base);
 
+/* The whole end-to-end step in one call: host RLE streams in (as vp_upload_chunks_rle), rebuild (as
+ * vp_rebuild_batch), host buffers out -- internally pipelined over `n_blocks` blocks of ascending chunk ids on three
+ * streams (upload+decode | kernels | download) so PCIe runs in both directions at once.  n_blocks = 1, or ids not
+ * ascending, degenerates to the sequential order.  Results are identical to the two separate calls. */
+VP_API int  vp_rebuild_from_rle(vp_ctx *ctx, const uint32_t *chunk_ids, uint32_t n, const uint32_t *words,
+                         const uint64_t *word_offsets, uint32_t flags, const uint8_t *per_chunk_flags, uint32_t n_blocks,
+                         vp_chunk_result *results, const void **splat_base, const void **mesh_base);
+
 /* Asynchronous device-resident variant (what the bench times as `value`): chunk ids are taken from
  * the host array once (vp_batch_prepare), kernels are enqueued on the context stream, outputs stay
  * in the device arenas.  vp_rebuild_device_results copies the per-chunk records back. */

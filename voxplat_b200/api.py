@@ -69,6 +69,7 @@ def load_library():
         "vp_rle_compress": (C.c_int, [vp, vp, C.c_uint32, vp, C.c_uint32, C.POINTER(C.c_uint32)]),
         "vp_rle_decompress": (C.c_int, [vp, vp, C.c_uint32, vp, C.c_uint32, C.POINTER(C.c_uint32)]),
         "vp_rebuild_batch": (C.c_int, [vp, vp, C.c_uint32, C.c_uint32, vp, vp, C.POINTER(vp), C.POINTER(vp)]),
+        "vp_rebuild_from_rle": (C.c_int, [vp, vp, C.c_uint32, vp, vp, C.c_uint32, vp, C.c_uint32, vp, C.POINTER(vp), C.POINTER(vp)]),
         "vp_batch_prepare": (C.c_int, [vp, vp, C.c_uint32, vp, C.c_uint32]),
         "vp_rebuild_device": (C.c_int, [vp]),
         "vp_rebuild_device_results": (C.c_int, [vp, vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
@@ -215,6 +216,22 @@ class Context:
         pcf = np.ascontiguousarray(per_chunk_flags, dtype=np.uint8) if per_chunk_flags is not None else None
         sb, mb = C.c_void_p(), C.c_void_p()
         self._ck(self.lib.vp_rebuild_batch(self.h, _ptr(ids), len(ids), flags, _ptr(pcf), _ptr(res), C.byref(sb), C.byref(mb)))
+        s_end = int((res["svl_offset"] + res["svl_items_total"].astype(np.uint64) * 2).max()) if len(ids) else 0
+        m_end = int(np.maximum(res["vbo_offset"] + res["vbo_items"].astype(np.uint64) * 2,
+                               res["ibo_offset"] + res["ibo_items"].astype(np.uint64) * 4).max()) if len(ids) else 0
+        splat = np.ctypeslib.as_array(C.cast(sb, C.POINTER(C.c_uint8)), shape=(s_end,)) if s_end and sb.value else np.zeros(0, np.uint8)
+        mesh = np.ctypeslib.as_array(C.cast(mb, C.POINTER(C.c_uint8)), shape=(m_end,)) if m_end and mb.value else np.zeros(0, np.uint8)
+        return res, splat, mesh
+
+    def rebuild_from_rle(self, ids, words, word_offsets, flags=VP_REBUILD_SPLAT, per_chunk_flags=None, n_blocks=8):
+        """Host RLE in -> host buffers out in one pipelined call (see vp_rebuild_from_rle)."""
+        ids = _u32(ids)
+        word_offsets = np.ascontiguousarray(word_offsets, dtype=np.uint64)
+        res = np.zeros(len(ids), RESULT_DTYPE)
+        pcf = np.ascontiguousarray(per_chunk_flags, dtype=np.uint8) if per_chunk_flags is not None else None
+        sb, mb = C.c_void_p(), C.c_void_p()
+        self._ck(self.lib.vp_rebuild_from_rle(self.h, _ptr(ids), len(ids), _ptr(words), _ptr(word_offsets), flags, _ptr(pcf), n_blocks,
+                                              _ptr(res), C.byref(sb), C.byref(mb)))
         s_end = int((res["svl_offset"] + res["svl_items_total"].astype(np.uint64) * 2).max()) if len(ids) else 0
         m_end = int(np.maximum(res["vbo_offset"] + res["vbo_items"].astype(np.uint64) * 2,
                                res["ibo_offset"] + res["ibo_items"].astype(np.uint64) * 4).max()) if len(ids) else 0

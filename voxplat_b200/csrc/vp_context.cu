@@ -105,6 +105,9 @@ static void ctx_free(vp_ctx *c)
 	cudaFreeHost(c->h_io_stage);
 	if (c->own_stream) cudaStreamDestroy(c->own_stream);
 	if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+	if (c->down_stream) cudaStreamDestroy(c->down_stream);
+	for (int k = 0; k < 2; k++) for (int i = 0; i < 64; i++) if (c->ev_pipe[k][i]) cudaEventDestroy(c->ev_pipe[k][i]);
+	cudaFreeHost(c->h_steps);
 	if (c->ev_a) cudaEventDestroy(c->ev_a);
 	if (c->ev_b) cudaEventDestroy(c->ev_b);
 	for (int h = 0; h < vp_ctx::kHist; h++) for (int i = 0; i < 4; i++) if (c->ev_k[h][i]) cudaEventDestroy(c->ev_k[h][i]);
@@ -145,6 +148,9 @@ extern "C" int vp_ctx_create(const vp_config *cfg, vp_ctx **out)
 	CK(cudaSetDevice(cfg->device));
 	CK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
 	CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+	CK(cudaStreamCreateWithFlags(&c->down_stream, cudaStreamNonBlocking));
+	for (int k = 0; k < 2; k++) for (int i = 0; i < 64; i++) CK(cudaEventCreateWithFlags(&c->ev_pipe[k][i], cudaEventDisableTiming));
+	CK(cudaHostAlloc(&c->h_steps, 64 * 2 * sizeof(VpArenaDev), cudaHostAllocDefault));
 	CK(cudaEventCreateWithFlags(&c->ev_a, cudaEventDisableTiming));
 	CK(cudaEventCreateWithFlags(&c->ev_b, cudaEventDisableTiming));
 	for (int h = 0; h < vp_ctx::kHist; h++) for (int i = 0; i < 4; i++) CK(cudaEventCreate(&c->ev_k[h][i]));
@@ -757,5 +763,170 @@ extern "C" int vp_rle_decompress(vp_ctx *c, const uint32_t *words, uint32_t n_wo
 	VP_CUDA(c, cudaMemcpyAsync(out, d_dst, total, cudaMemcpyDeviceToHost, c->stream));
 	VP_CUDA(c, cudaStreamSynchronize(c->stream));
 	if (status) return vp_fail(c, VP_ERR_RLE, "vp_rle_decompress: malformed stream");
+	return VP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Pipelined end-to-end rebuild: host RLE streams in, host buffers out, in ONE call.
+// Same result as vp_upload_chunks_rle + vp_rebuild_batch, but the batch is cut into blocks of ascending ids
+// that flow through three streams -- upload+decode | kernels | download -- so that the PCIe transfers of
+// different blocks run in both directions at once and hide the kernels.  Blocks are processed from the
+// HIGHEST ids down: the cull of a chunk reads its +x/+y/+z neighbours (larger ids), which are then already
+// decoded; the mesh of a chunk also reads neighbours with smaller ids, so it is launched in the step in
+// which the lowest of them (id - nx*ny - nx - 1) has been decoded.
+// ------------------------------------------------------------------------------------------------
+extern "C" int vp_rebuild_from_rle(vp_ctx *c, const uint32_t *ids, uint32_t n, const uint32_t *words, const uint64_t *word_offsets,
+                                   uint32_t flags, const uint8_t *per_chunk_flags, uint32_t n_blocks,
+                                   vp_chunk_result *results, const void **splat_base, const void **mesh_base)
+{
+	if (!c || !n || !ids || !words || !word_offsets || !results) return vp_fail(c, VP_ERR_ARG, "vp_rebuild_from_rle: null argument");
+	VP_CUDA(c, cudaSetDevice(c->cfg.device));
+	bool ascending = true;
+	for (uint32_t i = 1; i < n && ascending; i++) ascending = ids[i] > ids[i - 1];
+	if (!ascending || n_blocks < 1) n_blocks = 1;                    // pipelining needs ascending ids
+	n_blocks = std::min<uint32_t>(std::min<uint32_t>(n_blocks, 64u), n);
+	const uint32_t N = 1u << (3 * c->rb), per_row = (uint32_t)c->nx * c->ny;
+	const uint64_t total_words = word_offsets[n] - word_offsets[0];
+	if (total_words * 4 > c->cfg.rle_arena_bytes) return vp_fail(c, VP_ERR_ARENA_FULL, "vp_rebuild_from_rle: rle arena too small");
+	int rc = batch_reserve(c, n);
+	if (rc) return rc;
+
+	// ---- host bookkeeping for the whole batch ----
+	std::vector<uint8_t> want(n);
+	for (uint32_t i = 0; i < n; i++) {
+		if (word_offsets[i + 1] < word_offsets[i] + 2) return vp_fail(c, VP_ERR_RLE, "vp_rebuild_from_rle: stream shorter than 2 words");
+		want[i] = words[word_offsets[i]] != N;
+		const uint32_t cz = ids[i] / per_row;
+		if (ids[i] >= per_row * (uint32_t)c->nz || (int)cz < c->cfg.slab_z0 || (int)cz >= c->cfg.slab_z1)
+			return vp_fail(c, VP_ERR_NOT_RESIDENT, "vp_rebuild_from_rle: chunk id outside the owned slab");
+	}
+	std::vector<int32_t> slots;
+	if ((rc = assign_slots(c, ids, n, want.data(), slots))) return rc;
+	if ((rc = push_slot_table(c, ids, n))) return rc;
+	std::vector<unsigned long long> rel(n + 1);
+	for (uint32_t i = 0; i <= n; i++) rel[i] = word_offsets[i] - word_offsets[0];
+	const size_t off_bytes = (size_t)(n + 1) * 8, slot_bytes = (size_t)n * 4;
+	if ((rc = dio_reserve(c, off_bytes + slot_bytes + 16))) return rc;
+	unsigned long long *d_off = reinterpret_cast<unsigned long long *>(c->d_io);
+	int32_t *d_slots = reinterpret_cast<int32_t *>(c->d_io + off_bytes);
+	uint32_t *d_status = reinterpret_cast<uint32_t *>(c->d_io + off_bytes + ((slot_bytes + 7) & ~(size_t)7));
+	VP_CUDA(c, cudaMemcpyAsync(d_off, rel.data(), off_bytes, cudaMemcpyHostToDevice, c->stream));
+	VP_CUDA(c, cudaMemcpyAsync(d_slots, slots.data(), slot_bytes, cudaMemcpyHostToDevice, c->stream));
+	VP_CUDA(c, cudaMemsetAsync(d_status, 0, 4, c->stream));
+
+	// block b covers batch positions [bstart[b], bstart[b+1]); step t = 0.. processes block n_blocks-1-t
+	std::vector<uint32_t> bstart(n_blocks + 1);
+	for (uint32_t b = 0; b <= n_blocks; b++) bstart[b] = (uint32_t)((uint64_t)n * b / n_blocks);
+	auto slot_of = [&](uint32_t x, uint32_t y, uint32_t z) -> int32_t {
+		if (x >= (uint32_t)c->nx || y >= (uint32_t)c->ny || z >= (uint32_t)c->nz || (int)z < c->ez0 || (int)z >= c->ez1) return -1;
+		return c->h_slot[(size_t)(z - (uint32_t)c->ez0) * per_row + (size_t)y * c->nx + x];
+	};
+	std::vector<std::vector<uint32_t>> s_ids(n_blocks), s_pos(n_blocks), m_ids(n_blocks), m_pos(n_blocks);
+	for (uint32_t i = 0; i < n; i++) {
+		const uint32_t f = per_chunk_flags ? per_chunk_flags[i] : flags;
+		uint32_t b = (uint32_t)(std::upper_bound(bstart.begin(), bstart.end(), i) - bstart.begin()) - 1;
+		const uint32_t step = n_blocks - 1 - b;
+		if (f & VP_REBUILD_SPLAT) {
+			const uint32_t cx = ids[i] % (uint32_t)c->nx, cy = (ids[i] / (uint32_t)c->nx) % (uint32_t)c->ny, cz = ids[i] / per_row;
+			if (slot_of(cx, cy, cz) >= 0 || slot_of(cx + 1, cy, cz) >= 0 || slot_of(cx, cy + 1, cz) >= 0 || slot_of(cx, cy, cz + 1) >= 0) {
+				s_ids[step].push_back(ids[i]); s_pos[step].push_back(i);
+			}
+		}
+		if (f & VP_REBUILD_MESH) {
+			// the lowest neighbour id; the mesh may run once the block that holds it (or the first block) is decoded
+			const int64_t low = (int64_t)ids[i] - per_row - c->nx - 1;
+			uint32_t mb = 0;
+			if (low > (int64_t)ids[0]) {
+				const uint32_t pos = (uint32_t)(std::lower_bound(ids, ids + n, (uint32_t)low) - ids);
+				mb = (uint32_t)(std::upper_bound(bstart.begin(), bstart.end(), std::min(pos, n - 1)) - bstart.begin()) - 1;
+			}
+			const uint32_t mstep = n_blocks - 1 - std::min(mb, b);
+			m_ids[mstep].push_back(ids[i]); m_pos[mstep].push_back(i);
+		}
+	}
+	std::vector<uint32_t> sid, spos, mid, mpos, s_first(n_blocks + 1, 0), m_first(n_blocks + 1, 0);
+	for (uint32_t t = 0; t < n_blocks; t++) {
+		sid.insert(sid.end(), s_ids[t].begin(), s_ids[t].end()); spos.insert(spos.end(), s_pos[t].begin(), s_pos[t].end());
+		mid.insert(mid.end(), m_ids[t].begin(), m_ids[t].end()); mpos.insert(mpos.end(), m_pos[t].begin(), m_pos[t].end());
+		s_first[t + 1] = (uint32_t)sid.size(); m_first[t + 1] = (uint32_t)mid.size();
+	}
+	if (!sid.empty()) {
+		VP_CUDA(c, cudaMemcpyAsync(c->d_splat_ids, sid.data(), sid.size() * 4, cudaMemcpyHostToDevice, c->stream));
+		VP_CUDA(c, cudaMemcpyAsync(c->d_splat_pos, spos.data(), spos.size() * 4, cudaMemcpyHostToDevice, c->stream));
+	}
+	if (!mid.empty()) {
+		VP_CUDA(c, cudaMemcpyAsync(c->d_mesh_ids, mid.data(), mid.size() * 4, cudaMemcpyHostToDevice, c->stream));
+		VP_CUDA(c, cudaMemcpyAsync(c->d_mesh_pos, mpos.data(), mpos.size() * 4, cudaMemcpyHostToDevice, c->stream));
+	}
+	c->batch_n = n;
+	for (int a = 0; a < 3; a++) { c->h_arena_state[3 + a].cursor = 0; c->h_arena_state[3 + a].overflow = 0; c->h_arena_state[3 + a].pad = 0; }
+	c->h_arena_state[3].capacity = c->cfg.splat_arena_bytes;
+	c->h_arena_state[4].capacity = c->cfg.mesh_arena_bytes;
+	VP_CUDA(c, cudaMemcpyAsync(c->d_arena_state, c->h_arena_state + 3, 2 * sizeof(VpArenaDev), cudaMemcpyHostToDevice, c->stream));
+	VP_CUDA(c, cudaMemsetAsync(c->d_results, 0, (size_t)n * sizeof(VpResultDev), c->stream));
+	// staging sized from the previous call (grown afterwards if this batch turns out larger)
+	if ((rc = stage_reserve(c, &c->h_splat_stage, &c->splat_stage_cap, std::max<uint64_t>(c->last_splat_bytes + c->last_splat_bytes / 4, 32u << 20)))) return rc;
+	if ((rc = stage_reserve(c, &c->h_mesh_stage, &c->mesh_stage_cap, std::max<uint64_t>(c->last_mesh_bytes + c->last_mesh_bytes / 4, 32u << 20)))) return rc;
+	VP_CUDA(c, cudaEventRecord(c->ev_a, c->stream));
+	VP_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev_a, 0));
+
+	// ---- enqueue: upload+decode on copy_stream, kernels on the main stream ----
+	VpWorldDev w = vp_world_dev(c);
+	for (uint32_t t = 0; t < n_blocks; t++) {
+		const uint32_t b = n_blocks - 1 - t, i0 = bstart[b], i1 = bstart[b + 1];
+		const uint64_t w0 = rel[i0], w1 = rel[i1];
+		VP_CUDA(c, cudaMemcpyAsync(c->d_rle_arena + w0 * 4, words + word_offsets[0] + w0, (w1 - w0) * 4, cudaMemcpyHostToDevice, c->copy_stream));
+		VP_CUDA(c, vp_launch_rle_decode(reinterpret_cast<const uint32_t *>(c->d_rle_arena), d_off + i0, d_slots + i0, i1 - i0, c->vox_pool, N, d_status, c->copy_stream));
+		VP_CUDA(c, vp_launch_extract_xfaces(c->rb, c->vox_pool, c->xlo_pool, c->xhi_pool, d_slots + i0, i1 - i0, c->copy_stream));
+		VP_CUDA(c, cudaEventRecord(c->ev_pipe[0][t], c->copy_stream));
+		c->launches += 2;
+		VP_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_pipe[0][t], 0));
+		if (s_first[t + 1] > s_first[t]) {
+			VP_CUDA(c, vp_launch_splat(w, c->d_splat_ids + s_first[t], s_first[t + 1] - s_first[t], c->d_results, c->d_splat_pos + s_first[t], c->d_splat_arena, c->d_arena_state + 0, c->stream));
+			c->launches++;
+		}
+		if (m_first[t + 1] > m_first[t]) {
+			VP_CUDA(c, vp_launch_mesh(w, c->d_mesh_ids + m_first[t], m_first[t + 1] - m_first[t], c->d_results, c->d_mesh_pos + m_first[t], c->d_mesh_arena, c->d_arena_state + 1, c->stream));
+			c->launches++;
+		}
+		VP_CUDA(c, cudaMemcpyAsync(c->h_steps + 2 * t, c->d_arena_state, 2 * sizeof(VpArenaDev), cudaMemcpyDeviceToHost, c->stream));
+		VP_CUDA(c, cudaEventRecord(c->ev_pipe[1][t], c->stream));
+	}
+	VP_CUDA(c, cudaMemcpyAsync(c->h_results, c->d_results, (size_t)n * sizeof(VpResultDev), cudaMemcpyDeviceToHost, c->stream));
+
+	// ---- download every step's new output range as soon as its kernels are done ----
+	uint64_t done_s = 0, done_m = 0;
+	bool staged = true;
+	for (uint32_t t = 0; t < n_blocks; t++) {
+		VP_CUDA(c, cudaEventSynchronize(c->ev_pipe[1][t]));
+		const uint64_t cs = c->h_steps[2 * t].cursor, cm = c->h_steps[2 * t + 1].cursor;
+		if (c->h_steps[2 * t].overflow || c->h_steps[2 * t + 1].overflow) { staged = false; break; }
+		if (cs > c->splat_stage_cap || cm > c->mesh_stage_cap) { staged = false; continue; }       // staging too small: bulk copy below
+		if (!staged) continue;
+		VP_CUDA(c, cudaStreamWaitEvent(c->down_stream, c->ev_pipe[1][t], 0));
+		if (cs > done_s) VP_CUDA(c, cudaMemcpyAsync(c->h_splat_stage + done_s, c->d_splat_arena + done_s, cs - done_s, cudaMemcpyDeviceToHost, c->down_stream));
+		if (cm > done_m) VP_CUDA(c, cudaMemcpyAsync(c->h_mesh_stage + done_m, c->d_mesh_arena + done_m, cm - done_m, cudaMemcpyDeviceToHost, c->down_stream));
+		done_s = cs; done_m = cm;
+	}
+	VP_CUDA(c, cudaStreamSynchronize(c->stream));
+	VP_CUDA(c, cudaStreamSynchronize(c->down_stream));
+	uint32_t status = 0;
+	VP_CUDA(c, cudaMemcpy(&status, d_status, 4, cudaMemcpyDeviceToHost));
+	VP_CUDA(c, cudaMemcpy(c->h_arena_state, c->d_arena_state, 2 * sizeof(VpArenaDev), cudaMemcpyDeviceToHost));
+	if (status) return vp_fail(c, VP_ERR_RLE, "vp_rebuild_from_rle: a stream does not expand to exactly one chunk volume");
+	if (c->h_arena_state[0].overflow || c->h_arena_state[1].overflow)
+		return vp_fail(c, VP_ERR_ARENA_FULL, "output arena too small (cursor values give the required bytes)");
+	const uint64_t sb = c->h_arena_state[0].cursor, mb = c->h_arena_state[1].cursor;
+	c->last_splat_bytes = sb; c->last_mesh_bytes = mb;
+	if (!staged) {           // first call / grown world: size the staging now and copy in bulk
+		if ((rc = stage_reserve(c, &c->h_splat_stage, &c->splat_stage_cap, sb))) return rc;
+		if ((rc = stage_reserve(c, &c->h_mesh_stage, &c->mesh_stage_cap, mb))) return rc;
+		if (sb) VP_CUDA(c, cudaMemcpyAsync(c->h_splat_stage, c->d_splat_arena, sb, cudaMemcpyDeviceToHost, c->stream));
+		if (mb) VP_CUDA(c, cudaMemcpyAsync(c->h_mesh_stage, c->d_mesh_arena, mb, cudaMemcpyDeviceToHost, c->stream));
+		VP_CUDA(c, cudaStreamSynchronize(c->stream));
+	}
+	memcpy(results, c->h_results, (size_t)n * sizeof(VpResultDev));
+	if (splat_base) *splat_base = c->h_splat_stage;
+	if (mesh_base) *mesh_base = c->h_mesh_stage;
 	return VP_OK;
 }

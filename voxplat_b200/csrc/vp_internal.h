@@ -55,7 +55,10 @@ struct vp_ctx {
 	int ez0, ez1;                 // extended slab rows held on this device
 	uint32_t n_ext;               // chunks in the extended slab
 	cudaStream_t own_stream, stream;
-	cudaStream_t copy_stream;
+	cudaStream_t copy_stream, down_stream;
+	cudaEvent_t ev_pipe[2][64];   // [0] decode done, [1] kernels done, per pipeline step
+	VpArenaDev *h_steps;          // pinned: arena states after every pipeline step [64][2]
+	uint64_t last_splat_bytes, last_mesh_bytes;
 	cudaEvent_t ev_a, ev_b;
 	static constexpr int kHist = 256;
 	cudaEvent_t ev_k[kHist][4];   // timing events around the splat [0,1] and mesh [2,3] kernels of the last kHist rebuilds

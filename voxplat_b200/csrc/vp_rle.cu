@@ -76,7 +76,13 @@ k_rle_decode(const uint32_t *__restrict__ words, const unsigned long long *__res
 			const uint32_t o = g * 16;
 			uint32_t lo = 0, hi = tc;                  // largest k with s_start[k] <= o
 			while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (s_start[mid] <= o) lo = mid; else hi = mid; }
-			uint32_t k = lo, out[4] = {0, 0, 0, 0};
+			uint32_t k = lo;
+			if (s_start[k + 1] >= o + 16) {            // one run covers the whole group (air, solid interior): broadcast
+				const uint32_t v = (uint32_t)s_val[k] * 0x01010101u;
+				*reinterpret_cast<uint4 *>(dst + o) = make_uint4(v, v, v, v);
+				continue;
+			}
+			uint32_t out[4] = {0, 0, 0, 0};
 			#pragma unroll
 			for (int b = 0; b < 16; b++) {
 				while (o + b >= s_start[k + 1]) k++;
