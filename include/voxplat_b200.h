@@ -186,6 +186,23 @@ VP_API int64_t vp_chunk_make_splatlists(vp_ctx *ctx, uint32_t chunk_id, int16_t 
 VP_API int  vp_chunk_make_mesh(vp_ctx *ctx, uint32_t chunk_id, int16_t *geometry, uint64_t cap_geometry_items,
                         uint32_t *geometry_items, uint32_t *index, uint64_t cap_index_items, uint32_t *index_items);
 
+/* ---- LOD-node aggregation: the consumer right after the path ------------------------ */
+
+/* One octree node of LOD level `lod` = what gfx_update_svl builds into set->gsvl[lod][node] (gfx/vsplat.c:209-323):
+ * the level-`lod` splat segments of all member chunks, concatenated x outer / y / z inner. */
+typedef struct {
+	uint64_t offset;                /* bytes into the node buffer returned in *base */
+	uint32_t items;                 /* GeometrySVL.vbo_items (int16 units) */
+	uint32_t members;               /* chunks under the node */
+} vp_node_result;
+
+/* Gather every node of level `lod` on the device from the splat lists of the LAST rebuild (which must have covered
+ * all chunks of the world in id order).  nodes[flatten3(chunk offset >> lod, max_bitw - min(lod, max_bitw))];
+ * *n_nodes = number of nodes of the level.  base == NULL keeps the node buffers on the device only;
+ * kernel_ms (optional) receives the device time of the gather. */
+VP_API int  vp_build_lod_nodes(vp_ctx *ctx, uint32_t lod, vp_node_result *nodes, uint32_t cap_nodes, uint32_t *n_nodes,
+                        const void **base, float *kernel_ms);
+
 /* ---- multi-GPU slab borders (new: the reference is single-process) ----------------------------- */
 
 /* A border plane = for every chunk column (cx,cy) of one chunk row, one R*R-byte z-slice, packed

@@ -318,3 +318,32 @@ VO_EXPORT double vo_world_rebuild(const vo_world *w, const uint32_t *ids, uint32
 	}
 	return omp_get_wtime() - t0;
 }
+
+/*
+ * LOD-node aggregation (the gather loops of gfx_update_svl, gfx/vsplat.c:209-323): node `node` of
+ * level `lod` (index = flatten3(chunk offset >> lod, max_bitw - min(lod, max_bitw)), :214-229) concatenates the
+ * level-`lod` segment of every member chunk's splat list; members are visited x outer, y, z inner (:264-266) and a
+ * segment starts after the chunk's lower levels (:297-300).  svl[c] = chunk c's splat list, items = [n_chunks][5].
+ * Returns the node's int16 item count (GeometrySVL.vbo_items, :325); `out` may be NULL to only count.
+ */
+VO_EXPORT uint32_t vo_lod_node(const int32_t bits[3], int32_t lod, uint32_t node, const int16_t *const *svl,
+                               const uint32_t *items, int16_t *out)
+{
+	int32_t ob[3];
+	uint32_t o[3], lo[3], hi[3], total = 0;
+	for (int i = 0; i < 3; i++) ob[i] = bits[i] - (lod < bits[i] ? lod : bits[i]);
+	o[0] = node & ((1u << ob[0]) - 1); o[1] = (node >> ob[0]) & ((1u << ob[1]) - 1); o[2] = node >> (ob[0] + ob[1]);
+	for (int i = 0; i < 3; i++) {
+		lo[i] = o[i] << lod; hi[i] = (o[i] + 1) << lod;
+		if (hi[i] > (1u << bits[i])) hi[i] = 1u << bits[i];
+	}
+	for (uint32_t x = lo[0]; x < hi[0]; x++) for (uint32_t y = lo[1]; y < hi[1]; y++) for (uint32_t z = lo[2]; z < hi[2]; z++) {
+		uint32_t c = ((z << bits[1] | y) << bits[0]) | x, start = 0;
+		const uint32_t *it = items + (size_t)c * 5;
+		if (!it[lod]) continue;
+		for (int l = 0; l < lod; l++) start += it[l];
+		if (out) memcpy(out + total, svl[c] + start, (size_t)it[lod] * sizeof(int16_t));
+		total += it[lod];
+	}
+	return total;
+}

@@ -37,6 +37,7 @@ class VpConfig(C.Structure):
 RESULT_DTYPE = np.dtype([("svl_offset", "<u8"), ("svl_items", "<u4", (5,)), ("svl_items_total", "<u4"),
                          ("vbo_offset", "<u8"), ("ibo_offset", "<u8"), ("vbo_items", "<u4"), ("ibo_items", "<u4")])
 assert RESULT_DTYPE.itemsize == 56
+NODE_DTYPE = np.dtype([("offset", "<u8"), ("items", "<u4"), ("members", "<u4")])
 
 _lib = None
 
@@ -79,6 +80,7 @@ def load_library():
         "vp_arena_download": (C.c_int, [vp, C.c_int, vp, C.c_uint64]),
         "vp_chunk_make_splatlists": (C.c_int64, [vp, C.c_uint32, vp, C.c_uint64, vp]),
         "vp_chunk_make_mesh": (C.c_int, [vp, C.c_uint32, vp, C.c_uint64, C.POINTER(C.c_uint32), vp, C.c_uint64, C.POINTER(C.c_uint32)]),
+        "vp_build_lod_nodes": (C.c_int, [vp, C.c_uint32, vp, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(vp), C.POINTER(C.c_float)]),
         "vp_halo_plane_bytes": (C.c_uint64, [vp]),
         "vp_halo_pack": (C.c_int, [vp, C.c_int, vp]),
         "vp_halo_unpack": (C.c_int, [vp, C.c_int, vp]),
@@ -295,6 +297,23 @@ class Context:
         nv, ni = C.c_uint32(), C.c_uint32()
         self._ck(self.lib.vp_chunk_make_mesh(self.h, chunk_id, _ptr(vbo), vbo.size, C.byref(nv), _ptr(ibo), ibo.size, C.byref(ni)))
         return vbo[:nv.value].copy(), ibo[:ni.value].copy()
+
+    # ---- LOD-node aggregation (gfx_update_svl's gather) ------------------------------------------------
+    def build_lod_nodes(self, lod, download=True):
+        """Returns (nodes structured array, node buffer bytes or None, kernel ms)."""
+        nn = 1
+        for b in self.max_bitw:
+            nn <<= b - min(lod, b)
+        nodes = np.zeros(nn, NODE_DTYPE)
+        n = C.c_uint32()
+        base = C.c_void_p()
+        ms = C.c_float()
+        self._ck(self.lib.vp_build_lod_nodes(self.h, lod, _ptr(nodes), nn, C.byref(n), C.byref(base) if download else None, C.byref(ms)))
+        buf = None
+        if download:
+            end = int((nodes["offset"] + nodes["items"].astype(np.uint64) * 2)[nodes["items"] > 0].max()) if (nodes["items"] > 0).any() else 0
+            buf = np.ctypeslib.as_array(C.cast(base, C.POINTER(C.c_uint8)), shape=(end,)) if end else np.zeros(0, np.uint8)
+        return nodes, buf, float(ms.value)
 
     # ---- multi-GPU borders ----------------------------------------------------------------------------
     def halo_plane_bytes(self):

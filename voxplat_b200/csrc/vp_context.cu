@@ -100,7 +100,7 @@ static void ctx_free(vp_ctx *c)
 	cudaFree(c->d_ids); cudaFree(c->d_flags); cudaFree(c->d_splat_ids); cudaFree(c->d_mesh_ids); cudaFree(c->d_results);
 	cudaFree(c->d_splat_pos); cudaFree(c->d_mesh_pos);
 	cudaFree(c->d_splat_arena); cudaFree(c->d_mesh_arena); cudaFree(c->d_rle_arena); cudaFree(c->d_arena_state);
-	cudaFree(c->d_tmp_slots); cudaFree(c->d_io);
+	cudaFree(c->d_tmp_slots); cudaFree(c->d_io); cudaFree(c->d_node_arena); cudaFree(c->d_nodes); cudaFreeHost(c->h_node_stage);
 	cudaFreeHost(c->h_results); cudaFreeHost(c->h_arena_state); cudaFreeHost(c->h_splat_stage); cudaFreeHost(c->h_mesh_stage);
 	cudaFreeHost(c->h_io_stage);
 	if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -928,5 +928,48 @@ extern "C" int vp_rebuild_from_rle(vp_ctx *c, const uint32_t *ids, uint32_t n, c
 	memcpy(results, c->h_results, (size_t)n * sizeof(VpResultDev));
 	if (splat_base) *splat_base = c->h_splat_stage;
 	if (mesh_base) *mesh_base = c->h_mesh_stage;
+	return VP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// LOD-node aggregation (gfx_update_svl's gather, vsplat.c:209-323) over the results of the last rebuild
+// ------------------------------------------------------------------------------------------------
+extern "C" int vp_build_lod_nodes(vp_ctx *c, uint32_t lod, vp_node_result *nodes, uint32_t cap_nodes, uint32_t *n_nodes, const void **base, float *kernel_ms)
+{
+	if (!c || lod >= VP_MAX_LOD_LEVEL || !n_nodes) return vp_fail(c, VP_ERR_ARG, "vp_build_lod_nodes: bad argument");
+	VP_CUDA(c, cudaSetDevice(c->cfg.device));
+	if (c->cfg.slab_z0 != 0 || c->cfg.slab_z1 != c->nz) return vp_fail(c, VP_ERR_ARG, "vp_build_lod_nodes: needs a context that owns the whole world");
+	if (c->batch_n != (uint32_t)c->nx * c->ny * c->nz) return vp_fail(c, VP_ERR_ARG, "vp_build_lod_nodes: the last rebuild must have covered every chunk in id order");
+	const int bits[3] = { c->cfg.max_bitw[0], c->cfg.max_bitw[1], c->cfg.max_bitw[2] };
+	uint32_t nn = 1;
+	for (int i = 0; i < 3; i++) nn <<= bits[i] - std::min<int>((int)lod, bits[i]);
+	*n_nodes = nn;
+	if (!nodes || cap_nodes < nn) return vp_fail(c, VP_ERR_ARENA_FULL, "vp_build_lod_nodes: node table too small (*n_nodes entries needed)");
+	VP_CUDA(c, cudaStreamSynchronize(c->stream));
+	if (nn > c->nodes_cap) { cudaFree(c->d_nodes); c->d_nodes = nullptr; VP_CUDA(c, cudaMalloc(&c->d_nodes, (size_t)nn * sizeof(VpNodeDev))); c->nodes_cap = nn; }
+	// the level's segments can never exceed what the rebuild wrote
+	VP_CUDA(c, cudaMemcpy(c->h_arena_state, c->d_arena_state, sizeof(VpArenaDev), cudaMemcpyDeviceToHost));
+	const size_t need = std::max<size_t>(c->h_arena_state[0].cursor, 1u << 20);
+	if (need > c->node_arena_cap) { cudaFree(c->d_node_arena); c->d_node_arena = nullptr; VP_CUDA(c, cudaMalloc(&c->d_node_arena, need)); c->node_arena_cap = need; }
+	c->h_arena_state[5].cursor = 0; c->h_arena_state[5].capacity = c->node_arena_cap; c->h_arena_state[5].overflow = 0; c->h_arena_state[5].pad = 0;
+	VP_CUDA(c, cudaMemcpyAsync(c->d_arena_state + 2, c->h_arena_state + 5, sizeof(VpArenaDev), cudaMemcpyHostToDevice, c->stream));
+	VP_CUDA(c, cudaEventRecord(c->ev_k[0][0], c->stream));
+	VP_CUDA(c, vp_launch_lod_nodes((int)lod, bits, nn, c->d_results, c->d_splat_arena, c->d_node_arena, c->d_arena_state + 2, c->d_nodes, c->stream));
+	VP_CUDA(c, cudaEventRecord(c->ev_k[0][1], c->stream));
+	c->launches++;
+	static_assert(sizeof(vp_node_result) == sizeof(VpNodeDev), "node layout must match the C ABI");
+	VP_CUDA(c, cudaMemcpyAsync(nodes, c->d_nodes, (size_t)nn * sizeof(VpNodeDev), cudaMemcpyDeviceToHost, c->stream));
+	VP_CUDA(c, cudaMemcpyAsync(c->h_arena_state + 2, c->d_arena_state + 2, sizeof(VpArenaDev), cudaMemcpyDeviceToHost, c->stream));
+	VP_CUDA(c, cudaStreamSynchronize(c->stream));
+	if (kernel_ms) VP_CUDA(c, cudaEventElapsedTime(kernel_ms, c->ev_k[0][0], c->ev_k[0][1]));
+	if (c->h_arena_state[2].overflow) return vp_fail(c, VP_ERR_ARENA_FULL, "vp_build_lod_nodes: node arena overflow");
+	if (base) {
+		const uint64_t used = c->h_arena_state[2].cursor;
+		int rc = stage_reserve(c, &c->h_node_stage, &c->node_stage_cap, used);
+		if (rc) return rc;
+		if (used) VP_CUDA(c, cudaMemcpyAsync(c->h_node_stage, c->d_node_arena, used, cudaMemcpyDeviceToHost, c->stream));
+		VP_CUDA(c, cudaStreamSynchronize(c->stream));
+		*base = c->h_node_stage;
+	}
 	return VP_OK;
 }

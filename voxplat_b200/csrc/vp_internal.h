@@ -40,6 +40,13 @@ struct VpResultDev {
 };
 static_assert(sizeof(VpResultDev) == sizeof(vp_chunk_result), "result layout must match the C ABI");
 
+// Per-node record of the LOD aggregation (device mirror of vp_node_result).
+struct VpNodeDev {
+	unsigned long long offset;     // bytes into the node arena (~0 = not reserved)
+	uint32_t items;                // int16 items = GeometrySVL.vbo_items
+	uint32_t members;              // chunks under the node
+};
+
 // Arena bump allocator state in device memory.
 struct VpArenaDev {
 	unsigned long long cursor;     // bytes used
@@ -83,6 +90,8 @@ struct vp_ctx {
 	VpArenaDev *h_arena_state;    // pinned mirror
 	uint8_t *h_splat_stage, *h_mesh_stage; size_t splat_stage_cap, mesh_stage_cap;
 	uint8_t *h_io_stage; size_t io_stage_cap;            // pinned staging for uploads / rle
+	uint8_t *d_node_arena; size_t node_arena_cap; VpNodeDev *d_nodes; uint32_t nodes_cap;   // LOD-node aggregation (vp_nodes.cu)
+	uint8_t *h_node_stage; size_t node_stage_cap;
 	uint8_t *d_io; size_t d_io_cap;                      // device scratch for the flat RLE codec / stream offsets
 	uint64_t launches;
 	std::string err;
@@ -103,3 +112,5 @@ cudaError_t vp_launch_rle_decode(const uint32_t *d_words, const unsigned long lo
                                  uint32_t n, uint8_t *dst_base, uint32_t N, uint32_t *d_status, cudaStream_t s);
 cudaError_t vp_launch_rle_encode(const uint8_t *src_base, const int32_t *d_slots, uint32_t n, uint32_t N, uint32_t *d_arena_words,
                                  VpArenaDev *state, unsigned long long *d_offsets, uint32_t *d_counts, cudaStream_t s);
+cudaError_t vp_launch_lod_nodes(int lod, const int bits[3], uint32_t n_nodes, const VpResultDev *d_chunk_res, const uint8_t *d_splat_arena,
+                                uint8_t *d_node_arena, VpArenaDev *state, VpNodeDev *d_nodes, cudaStream_t s);
