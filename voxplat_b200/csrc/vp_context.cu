@@ -954,9 +954,11 @@ extern "C" int vp_build_lod_nodes(vp_ctx *c, uint32_t lod, vp_node_result *nodes
 	c->h_arena_state[5].cursor = 0; c->h_arena_state[5].capacity = c->node_arena_cap; c->h_arena_state[5].overflow = 0; c->h_arena_state[5].pad = 0;
 	VP_CUDA(c, cudaMemcpyAsync(c->d_arena_state + 2, c->h_arena_state + 5, sizeof(VpArenaDev), cudaMemcpyHostToDevice, c->stream));
 	VP_CUDA(c, cudaEventRecord(c->ev_k[0][0], c->stream));
-	VP_CUDA(c, vp_launch_lod_nodes((int)lod, bits, nn, c->d_results, c->d_splat_arena, c->d_node_arena, c->d_arena_state + 2, c->d_nodes, c->stream));
+	{ int rc2 = dio_reserve(c, (size_t)c->batch_n * 8); if (rc2) return rc2; }
+	VP_CUDA(c, vp_launch_lod_nodes((int)lod, bits, nn, c->d_results, c->d_splat_arena, c->d_node_arena, c->d_arena_state + 2, c->d_nodes,
+	                               reinterpret_cast<unsigned long long *>(c->d_io), c->stream));
 	VP_CUDA(c, cudaEventRecord(c->ev_k[0][1], c->stream));
-	c->launches++;
+	c->launches += 2;
 	static_assert(sizeof(vp_node_result) == sizeof(VpNodeDev), "node layout must match the C ABI");
 	VP_CUDA(c, cudaMemcpyAsync(nodes, c->d_nodes, (size_t)nn * sizeof(VpNodeDev), cudaMemcpyDeviceToHost, c->stream));
 	VP_CUDA(c, cudaMemcpyAsync(c->h_arena_state + 2, c->d_arena_state + 2, sizeof(VpArenaDev), cudaMemcpyDeviceToHost, c->stream));

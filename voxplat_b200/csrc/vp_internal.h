@@ -113,4 +113,4 @@ cudaError_t vp_launch_rle_decode(const uint32_t *d_words, const unsigned long lo
 cudaError_t vp_launch_rle_encode(const uint8_t *src_base, const int32_t *d_slots, uint32_t n, uint32_t N, uint32_t *d_arena_words,
                                  VpArenaDev *state, unsigned long long *d_offsets, uint32_t *d_counts, cudaStream_t s);
 cudaError_t vp_launch_lod_nodes(int lod, const int bits[3], uint32_t n_nodes, const VpResultDev *d_chunk_res, const uint8_t *d_splat_arena,
-                                uint8_t *d_node_arena, VpArenaDev *state, VpNodeDev *d_nodes, cudaStream_t s);
+                                uint8_t *d_node_arena, VpArenaDev *state, VpNodeDev *d_nodes, unsigned long long *d_chunk_dst, cudaStream_t s);

@@ -8,8 +8,9 @@
 // re-uploads it whenever one member changes; here all nodes of a level are gathered on the device in one
 // launch straight from the splat arena the rebuild wrote.
 //
-// One CTA per node: member sizes -> block prefix scan (stable member order) -> one arena reservation ->
-// coalesced 8-byte copies (every splat is 8 bytes, so all segment boundaries are 8-byte aligned).
+// Plan kernel, one CTA per node: member sizes -> block prefix scan (stable member order) -> one arena reservation
+// -> destination of every member chunk.  Copy kernel, one CTA per chunk: coalesced 8-byte copies (every splat is
+// 8 bytes, so all segment boundaries are 8-byte aligned).
 #include "vp_device.cuh"
 using namespace vp;
 
@@ -18,8 +19,8 @@ namespace {
 constexpr int kT = 256;
 
 __global__ void __launch_bounds__(kT)
-k_lod_nodes(int lod, int bx, int by, int bz, const VpResultDev *__restrict__ chunk_res, const uint8_t *__restrict__ splat_arena,
-            uint8_t *__restrict__ node_arena, VpArenaDev *__restrict__ st, VpNodeDev *__restrict__ nodes)
+k_lod_nodes_plan(int lod, int bx, int by, int bz, const VpResultDev *__restrict__ chunk_res,
+            VpArenaDev *__restrict__ st, VpNodeDev *__restrict__ nodes, unsigned long long *__restrict__ chunk_dst)
 {
 	__shared__ uint32_t s_pre[4096 + 1];          // member prefix (items); 8^4 members at most
 	__shared__ uint32_t s_wsum[kT / 32];
@@ -69,26 +70,36 @@ k_lod_nodes(int lod, int bx, int by, int bz, const VpResultDev *__restrict__ chu
 		nodes[node].members = nm;
 	}
 	__syncthreads();
-	if (!total || s_off == ~0ull) return;
-	unsigned long long *dst = reinterpret_cast<unsigned long long *>(node_arena + s_off);
-	for (uint32_t m = 0; m < nm; m++) {
-		const uint32_t n8 = (s_pre[m + 1] - s_pre[m]) >> 2;          // 8-byte records of this member
-		if (!n8) continue;
-		const VpResultDev &r = chunk_res[member_chunk(m)];
-		uint32_t start = 0;
-		for (int l = 0; l < lod; l++) start += r.svl_items[l];       // vsplat.c:297-300
-		const unsigned long long *src = reinterpret_cast<const unsigned long long *>(splat_arena + r.svl_offset) + (start >> 2);
-		unsigned long long *d = dst + (s_pre[m] >> 2);
-		for (uint32_t i = tid; i < n8; i += kT) d[i] = __ldg(src + i);
-	}
+	// plan only: every member learns where its segment goes; the copy runs with one CTA per CHUNK so that the
+	// few, huge nodes of the high levels are gathered by the whole GPU instead of one CTA each
+	for (uint32_t m = tid; m < nm; m += kT)
+		chunk_dst[member_chunk(m)] = (total && s_off != ~0ull && s_pre[m + 1] != s_pre[m]) ? s_off + (unsigned long long)s_pre[m] * 2ull : ~0ull;
+}
+
+__global__ void __launch_bounds__(kT)
+k_lod_nodes_copy(int lod, const VpResultDev *__restrict__ chunk_res, const uint8_t *__restrict__ splat_arena,
+                 uint8_t *__restrict__ node_arena, const unsigned long long *__restrict__ chunk_dst)
+{
+	const unsigned long long off = chunk_dst[blockIdx.x];
+	if (off == ~0ull) return;
+	const VpResultDev &r = chunk_res[blockIdx.x];
+	uint32_t start = 0;
+	for (int l = 0; l < lod; l++) start += r.svl_items[l];           // vsplat.c:297-300
+	const uint32_t n8 = r.svl_items[lod] >> 2;                       // 8-byte splat records
+	const unsigned long long *src = reinterpret_cast<const unsigned long long *>(splat_arena + r.svl_offset) + (start >> 2);
+	unsigned long long *dst = reinterpret_cast<unsigned long long *>(node_arena + off);
+	for (uint32_t i = threadIdx.x; i < n8; i += kT) dst[i] = __ldg(src + i);
 }
 
 } // namespace
 
 cudaError_t vp_launch_lod_nodes(int lod, const int bits[3], uint32_t n_nodes, const VpResultDev *d_chunk_res, const uint8_t *d_splat_arena,
-                                uint8_t *d_node_arena, VpArenaDev *state, VpNodeDev *d_nodes, cudaStream_t s)
+                                uint8_t *d_node_arena, VpArenaDev *state, VpNodeDev *d_nodes, unsigned long long *d_chunk_dst, cudaStream_t s)
 {
 	if (!n_nodes) return cudaSuccess;
-	k_lod_nodes<<<n_nodes, kT, 0, s>>>(lod, bits[0], bits[1], bits[2], d_chunk_res, d_splat_arena, d_node_arena, state, d_nodes);
+	k_lod_nodes_plan<<<n_nodes, kT, 0, s>>>(lod, bits[0], bits[1], bits[2], d_chunk_res, state, d_nodes, d_chunk_dst);
+	cudaError_t e = cudaGetLastError();
+	if (e != cudaSuccess) return e;
+	k_lod_nodes_copy<<<1u << (bits[0] + bits[1] + bits[2]), kT, 0, s>>>(lod, d_chunk_res, d_splat_arena, d_node_arena, d_chunk_dst);
 	return cudaGetLastError();
 }
