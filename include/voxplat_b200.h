@@ -186,6 +186,18 @@ VP_API int64_t vp_chunk_make_splatlists(vp_ctx *ctx, uint32_t chunk_id, int16_t 
 VP_API int  vp_chunk_make_mesh(vp_ctx *ctx, uint32_t chunk_id, int16_t *geometry, uint64_t cap_geometry_items,
                         uint32_t *geometry_items, uint32_t *index, uint64_t cap_index_items, uint32_t *index_items);
 
+/* ---- device-side edits ------------------------------------------------------------ */
+
+/* chunkset_edit_sphere (chunkset/edit.c:179-244) on the device copy: writes `voxel` into every cell closer than
+ * `radius` to (x,y,z) (cells with y < 2 are protected, edit.c:151), applies shadow_place_update (shadow.h:77-89) in
+ * the reference's order when voxel != 0, refreshes the x-face planes.  dirty_ids receives the chunks the reference
+ * marks dirty (all chunks of the box [c-r-1, c+r+1], in its list order); *n_dirty their number.  The caller
+ * rebuilds them with vp_rebuild_batch.  No voxel data crosses PCIe. */
+VP_API int  vp_edit_sphere(vp_ctx *ctx, int32_t x, int32_t y, int32_t z, uint32_t radius, uint8_t voxel,
+                    uint32_t *dirty_ids, uint32_t cap, uint32_t *n_dirty);
+/* Read height-map rows [z0,z1) back (the device copy is authoritative after vp_edit_sphere). */
+VP_API int  vp_download_shadow_rows(vp_ctx *ctx, uint32_t z0, uint32_t z1, uint16_t *rows);
+
 /* ---- LOD-node aggregation: the consumer right after the path ------------------------ */
 
 /* One octree node of LOD level `lod` = what gfx_update_svl builds into set->gsvl[lod][node] (gfx/vsplat.c:209-323):

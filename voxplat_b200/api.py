@@ -80,6 +80,8 @@ def load_library():
         "vp_arena_download": (C.c_int, [vp, C.c_int, vp, C.c_uint64]),
         "vp_chunk_make_splatlists": (C.c_int64, [vp, C.c_uint32, vp, C.c_uint64, vp]),
         "vp_chunk_make_mesh": (C.c_int, [vp, C.c_uint32, vp, C.c_uint64, C.POINTER(C.c_uint32), vp, C.c_uint64, C.POINTER(C.c_uint32)]),
+        "vp_edit_sphere": (C.c_int, [vp, C.c_int32, C.c_int32, C.c_int32, C.c_uint32, C.c_uint8, vp, C.c_uint32, C.POINTER(C.c_uint32)]),
+        "vp_download_shadow_rows": (C.c_int, [vp, C.c_uint32, C.c_uint32, vp]),
         "vp_build_lod_nodes": (C.c_int, [vp, C.c_uint32, vp, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(vp), C.POINTER(C.c_float)]),
         "vp_halo_plane_bytes": (C.c_uint64, [vp]),
         "vp_halo_pack": (C.c_int, [vp, C.c_int, vp]),
@@ -297,6 +299,20 @@ class Context:
         nv, ni = C.c_uint32(), C.c_uint32()
         self._ck(self.lib.vp_chunk_make_mesh(self.h, chunk_id, _ptr(vbo), vbo.size, C.byref(nv), _ptr(ibo), ibo.size, C.byref(ni)))
         return vbo[:nv.value].copy(), ibo[:ni.value].copy()
+
+    # ---- device-side edits (chunkset_edit_sphere) ----------------------------------------------------------
+    def edit_sphere(self, x, y, z, radius, voxel):
+        """Returns the dirty chunk ids (the reference's list, in its order)."""
+        ids = np.zeros(1024, np.uint32)
+        n = C.c_uint32()
+        self._ck(self.lib.vp_edit_sphere(self.h, x, y, z, radius, voxel, _ptr(ids), ids.size, C.byref(n)))
+        return ids[:n.value].copy()
+
+    def download_shadow_rows(self, z0, z1):
+        shw = ((1 << self.max_bitw[0]) + (1 << self.max_bitw[1])) << self.root_bitw
+        rows = np.zeros((z1 - z0) * shw, np.uint16)
+        self._ck(self.lib.vp_download_shadow_rows(self.h, z0, z1, _ptr(rows)))
+        return rows
 
     # ---- LOD-node aggregation (gfx_update_svl's gather) ------------------------------------------------
     def build_lod_nodes(self, lod, download=True):

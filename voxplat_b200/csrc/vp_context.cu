@@ -975,3 +975,53 @@ extern "C" int vp_build_lod_nodes(vp_ctx *c, uint32_t lod, vp_node_result *nodes
 	}
 	return VP_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Device-side brush edit (chunkset_edit_sphere, edit.c:179-244) and height-map read-back
+// ------------------------------------------------------------------------------------------------
+extern "C" int vp_edit_sphere(vp_ctx *c, int32_t x, int32_t y, int32_t z, uint32_t radius, uint8_t voxel,
+                              uint32_t *dirty_ids, uint32_t cap, uint32_t *n_dirty)
+{
+	if (!c || !n_dirty || radius > 64) return vp_fail(c, VP_ERR_ARG, "vp_edit_sphere: bad argument (radius <= 64)");
+	VP_CUDA(c, cudaSetDevice(c->cfg.device));
+	const int rb = c->rb;
+	const size_t N = (size_t)1 << (3 * rb);
+	// chunks in the box (chunkset_get_chunks_in_aabb, edit.c:89-126: inclusive chunk range of [c-r-1, c+r+1], x,y,z loops)
+	const int r = (int)radius;
+	const int lo[3] = { (x - r - 1) >> rb, (y - r - 1) >> rb, (z - r - 1) >> rb }, hi[3] = { (x + r + 1) >> rb, (y + r + 1) >> rb, (z + r + 1) >> rb };
+	std::vector<uint32_t> ids;
+	for (int gx = lo[0]; gx <= hi[0]; gx++) for (int gy = lo[1]; gy <= hi[1]; gy++) for (int gz = lo[2]; gz <= hi[2]; gz++) {
+		if (gx < 0 || gy < 0 || gz < 0 || gx >= c->nx || gy >= c->ny || gz >= c->nz) continue;
+		ids.push_back(((uint32_t)gz * c->ny + (uint32_t)gy) * c->nx + (uint32_t)gx);
+	}
+	*n_dirty = (uint32_t)ids.size();
+	if (ids.empty()) return VP_OK;                                  // edit.c:204-205
+	if (dirty_ids && cap >= ids.size()) memcpy(dirty_ids, ids.data(), ids.size() * 4);
+	// chunk_open_rw on a null chunk makes a fresh all-air copy (chunkset.c:174-180): give owned box chunks a zeroed slot
+	std::vector<uint32_t> own;
+	for (uint32_t id : ids) { const int cz = (int)(id / ((uint32_t)c->nx * c->ny)); if (cz >= c->cfg.slab_z0 && cz < c->cfg.slab_z1) own.push_back(id); }
+	std::vector<int32_t> before(own.size()), slots;
+	for (size_t i = 0; i < own.size(); i++) before[i] = c->h_slot[(size_t)ext_index(c, own[i])];
+	std::vector<uint8_t> want(own.size(), 1);
+	int rc = assign_slots(c, own.data(), (uint32_t)own.size(), want.data(), slots);
+	if (rc) return rc;
+	for (size_t i = 0; i < own.size(); i++) if (before[i] < 0) VP_CUDA(c, cudaMemsetAsync(c->vox_pool + (size_t)slots[i] * N, 0, N, c->stream));
+	if ((rc = push_slot_table(c, own.data(), (uint32_t)own.size()))) return rc;
+	VpWorldDev w = vp_world_dev(c);
+	VP_CUDA(c, vp_launch_edit_sphere(w, c->vox_pool, c->d_shadow, x, y, z, r, voxel, c->cfg.slab_z0, c->cfg.slab_z1, c->stream));
+	VP_CUDA(c, cudaMemcpyAsync(c->d_tmp_slots, slots.data(), slots.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+	VP_CUDA(c, vp_launch_extract_xfaces(c->rb, c->vox_pool, c->xlo_pool, c->xhi_pool, c->d_tmp_slots, (uint32_t)slots.size(), c->stream));
+	c->launches += 2;
+	VP_CUDA(c, cudaStreamSynchronize(c->stream));                   // `slots` goes out of scope
+	return VP_OK;
+}
+
+extern "C" int vp_download_shadow_rows(vp_ctx *c, uint32_t z0, uint32_t z1, uint16_t *rows)
+{
+	if (!c || !rows || z1 < z0 || z0 < c->sh_z0 || z1 > c->sh_z1) return vp_fail(c, VP_ERR_ARG, "vp_download_shadow_rows: rows outside the slab's range");
+	VP_CUDA(c, cudaSetDevice(c->cfg.device));
+	const uint32_t shw = (uint32_t)((c->nx + c->ny) << c->rb);
+	if (z1 > z0) VP_CUDA(c, cudaMemcpyAsync(rows, c->d_shadow + (size_t)(z0 - c->sh_z0) * shw, (size_t)(z1 - z0) * shw * 2, cudaMemcpyDeviceToHost, c->stream));
+	VP_CUDA(c, cudaStreamSynchronize(c->stream));
+	return VP_OK;
+}
