@@ -35,6 +35,30 @@ def sphere_edit(w, cx, cy, cz, r, v):
     return np.array(sorted(dirty), np.uint32)
 
 
+def run_device(rb, bits, bursts):
+    """Same bursts with the edit applied on the device (vp_edit_sphere): no voxel upload at all."""
+    w = worldgen.World(1234, rb, bits)
+    ctx = vpb.Context(rb, bits, mesh_arena_bytes=1 << 30, splat_arena_bytes=1 << 30)
+    nn = w.nonnull_ids()
+    ctx.upload_chunks_dense(nn, np.ascontiguousarray(w.dense[nn]))
+    ctx.upload_shadow_rows(0, w.shadow[:w.shw * w.dims[2]])
+    rng = np.random.default_rng(5)
+    X, Y, Z = w.dims
+    lat, nd = [], 0
+    for b in range(bursts):
+        x, z = int(rng.integers(8, X - 8)), int(rng.integers(8, Z - 8))
+        h = int(worldgen.lib().vpw_height(__import__("ctypes").byref(worldgen.params(1234, rb, bits)), x, z))
+        t0 = time.perf_counter()
+        dirty = ctx.edit_sphere(x, h, z, 4, 63 if b % 2 == 0 else 0)
+        res, splat, mesh = ctx.rebuild_batch(dirty, vpb.VP_REBUILD_SPLAT | vpb.VP_REBUILD_MESH)
+        lat.append((time.perf_counter() - t0) * 1e3)
+        nd += len(dirty)
+    ctx.close()
+    lat = np.array(lat[5:])
+    return {"chunk": 1 << rb, "mode": "edit on device", "ms_per_burst_median": float(np.median(lat)), "ms_per_burst_p95": float(np.percentile(lat, 95)),
+            "dirty_chunks_per_burst": nd / bursts}
+
+
 def run(rb, bits, bursts):
     w = worldgen.World(1234, rb, bits)
     ctx = vpb.Context(rb, bits, mesh_arena_bytes=1 << 30, splat_arena_bytes=1 << 30)
@@ -63,5 +87,5 @@ def run(rb, bits, bursts):
 
 
 if __name__ == "__main__":
-    out = [run(5, (4, 2, 4), 200), run(7, (3, 1, 3), 200)]
+    out = [run(5, (4, 2, 4), 200), run(7, (3, 1, 3), 200), run_device(5, (4, 2, 4), 200), run_device(7, (3, 1, 3), 200)]
     print(json.dumps(out))
