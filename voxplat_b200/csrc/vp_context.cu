@@ -77,17 +77,6 @@ __global__ void k_plane_copy(int rb, uint8_t *__restrict__ vox_pool, const int32
 	for (int i = threadIdx.x; i < RR / 16; i += blockDim.x) { if (unpack) sl[i] = pl[i]; else pl[i] = sl[i]; }
 }
 
-// any-nonzero test per chunk column of a received plane (decides which ghost chunks need a slot)
-__global__ void k_plane_nonzero(int rb, const uint8_t *__restrict__ plane, uint32_t *__restrict__ flags)
-{
-	const int RR = 1 << (2 * rb);
-	const uint4 *pl = reinterpret_cast<const uint4 *>(plane + (size_t)blockIdx.x * RR);
-	uint32_t any = 0;
-	for (int i = threadIdx.x; i < RR / 16; i += blockDim.x) { uint4 v = pl[i]; any |= v.x | v.y | v.z | v.w; }
-	any = __syncthreads_or(any != 0);
-	if (threadIdx.x == 0) flags[blockIdx.x] = any;
-}
-
 // ------------------------------------------------------------------------------------------------
 // context
 // ------------------------------------------------------------------------------------------------
