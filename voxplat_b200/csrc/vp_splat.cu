@@ -61,15 +61,16 @@ template <int RB> struct Geo {
 	static constexpr int NG = grp_off(5);
 	// shared memory carve-up (bytes)
 	static constexpr int RING_BYTES = kRing * TILE;
-	static constexpr int SCRATCH0 = (RING_BYTES + 127) / 128 * 128;
+	// the level bit arrays are built after the ring is drained, so they live in the same bytes
+	static constexpr int SCRATCH0 = ((RING_BYTES > LV_WORDS * 8 ? RING_BYTES : LV_WORDS * 8) + 127) / 128 * 128;
 	static constexpr int HALO_BYTES = 2 * ZS * R;
 	static constexpr int OCC_WORDS = NSL * (R + 1) * NW;
 	static constexpr int OCCX_WORDS = ZS * NW;
 	static constexpr int OFF_HALO = SCRATCH0;
 	static constexpr int OFF_OCC = OFF_HALO + HALO_BYTES;
 	static constexpr int OFF_OCCX = OFF_OCC + OCC_WORDS * 8;
-	static constexpr int OFF_LV = OFF_OCCX + OCCX_WORDS * 8;
-	static constexpr int OFF_BARS = OFF_LV + LV_WORDS * 8;
+	static constexpr int OFF_LV = 0;
+	static constexpr int OFF_BARS = OFF_OCCX + OCCX_WORDS * 8;
 	static constexpr int OFF_MISC = OFF_BARS + (2 * kRing + 1) * 8;
 	static constexpr int SMEM = OFF_MISC + 128 + (NG + 1) * 4;
 };
@@ -237,7 +238,7 @@ __device__ __forceinline__ void emit_group(const Ctx<RB> &cx, const uint64_t *lv
 }
 
 template <int RB>
-__global__ void __launch_bounds__(kThreads, RB <= 6 ? 5 : 1)
+__global__ void __launch_bounds__(kThreads, RB <= 6 ? 5 : 2)
 k_splat(const VpWorldDev w, const uint32_t *__restrict__ ids, VpResultDev *__restrict__ results,
         const uint32_t *__restrict__ result_pos, uint8_t *__restrict__ arena, VpArenaDev *__restrict__ st)
 {
