@@ -18,4 +18,4 @@ for _ in range(5): ctx.rebuild_device()
 lib.vp_debug_phase_cycles(out, 1)
 v = np.array(list(out), dtype=np.float64)
 names = ["0 init/zero", "1 stream+bits", "2 zero lv + vis", "3 LOD", "4 counts+scan", "5 cluster exchange", "6 emission", "-"]
-for n, x in zip(names, v): print("%-22s %6.1f%%  %8.0f cycles/CTA" % (n, 100 * x / v.sum(), x / 5 / (4 * len(nn))))
+for n, x in zip(names, v): print("%-22s %6.1f%%  %8.0f cycles/CTA" % (n, 100 * x / v.sum(), x / 5 / (int(os.environ.get("CL", 4)) * len(nn))))

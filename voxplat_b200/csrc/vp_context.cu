@@ -89,6 +89,7 @@ static void ctx_free(vp_ctx *c)
 	cudaFree(c->d_ids); cudaFree(c->d_flags); cudaFree(c->d_splat_ids); cudaFree(c->d_mesh_ids); cudaFree(c->d_results);
 	cudaFree(c->d_splat_pos); cudaFree(c->d_mesh_pos);
 	cudaFree(c->d_splat_arena); cudaFree(c->d_mesh_arena); cudaFree(c->d_rle_arena); cudaFree(c->d_arena_state);
+	cudaFree(c->d_splat_scratch);
 	cudaFree(c->d_tmp_slots); cudaFree(c->d_io); cudaFree(c->d_node_arena); cudaFree(c->d_nodes); cudaFreeHost(c->h_node_stage);
 	cudaFreeHost(c->h_results); cudaFreeHost(c->h_arena_state); cudaFreeHost(c->h_splat_stage); cudaFreeHost(c->h_mesh_stage);
 	cudaFreeHost(c->h_io_stage);
@@ -360,6 +361,18 @@ static int batch_reserve(vp_ctx *c, uint32_t n)
 	return VP_OK;
 }
 
+// Scratch between the count / scan / emit kernels of a splat rebuild of up to n chunks per launch.
+static int splat_scratch_reserve(vp_ctx *c, uint32_t n)
+{
+	const size_t need = vp_splat_scratch_bytes(c->rb, n);
+	if (need <= c->splat_scratch_cap) return VP_OK;
+	VP_CUDA(c, cudaStreamSynchronize(c->stream));
+	cudaFree(c->d_splat_scratch); c->d_splat_scratch = nullptr; c->splat_scratch_cap = 0;
+	VP_CUDA(c, cudaMalloc(&c->d_splat_scratch, need));
+	c->splat_scratch_cap = need;
+	return VP_OK;
+}
+
 extern "C" int vp_batch_prepare(vp_ctx *c, const uint32_t *ids, uint32_t n, const uint8_t *per_chunk_flags, uint32_t flags)
 {
 	if (!c || (n && !ids)) return vp_fail(c, VP_ERR_ARG, "vp_batch_prepare: null argument");
@@ -387,6 +400,7 @@ extern "C" int vp_batch_prepare(vp_ctx *c, const uint32_t *ids, uint32_t n, cons
 		if (f & VP_REBUILD_MESH) { mid.push_back(ids[i]); mpos.push_back(i); }
 	}
 	c->batch_n = n; c->n_splat = (uint32_t)sid.size(); c->n_mesh = (uint32_t)mid.size();
+	if ((rc = splat_scratch_reserve(c, c->n_splat))) return rc;
 	if (c->n_splat) {
 		VP_CUDA(c, cudaMemcpyAsync(c->d_splat_ids, sid.data(), sid.size() * 4, cudaMemcpyHostToDevice, c->stream));
 		VP_CUDA(c, cudaMemcpyAsync(c->d_splat_pos, spos.data(), spos.size() * 4, cudaMemcpyHostToDevice, c->stream));
@@ -417,10 +431,10 @@ extern "C" int vp_rebuild_device(vp_ctx *c)
 	c->rebuilds++;
 	if (c->n_splat) {
 		VP_CUDA(c, cudaEventRecord(ev[0], c->stream));
-		VP_CUDA(c, vp_launch_splat(w, c->d_splat_ids, c->n_splat, c->d_results, c->d_splat_pos, c->d_splat_arena, c->d_arena_state + 0, c->stream));
+		VP_CUDA(c, vp_launch_splat(w, c->d_splat_ids, c->n_splat, c->d_results, c->d_splat_pos, c->d_splat_arena, c->d_arena_state + 0, c->d_splat_scratch, c->stream));
 		VP_CUDA(c, cudaEventRecord(ev[1], c->stream));
 		valid |= 1;
-		c->launches++;
+		c->launches += kSplatLaunches;
 	}
 	if (c->n_mesh) {
 		VP_CUDA(c, cudaEventRecord(ev[2], c->stream));
@@ -839,6 +853,11 @@ extern "C" int vp_rebuild_from_rle(vp_ctx *c, const uint32_t *ids, uint32_t n, c
 		mid.insert(mid.end(), m_ids[t].begin(), m_ids[t].end()); mpos.insert(mpos.end(), m_pos[t].begin(), m_pos[t].end());
 		s_first[t + 1] = (uint32_t)sid.size(); m_first[t + 1] = (uint32_t)mid.size();
 	}
+	{
+		uint32_t largest = 0;
+		for (uint32_t t = 0; t < n_blocks; t++) largest = std::max(largest, s_first[t + 1] - s_first[t]);
+		if ((rc = splat_scratch_reserve(c, largest))) return rc;
+	}
 	if (!sid.empty()) {
 		VP_CUDA(c, cudaMemcpyAsync(c->d_splat_ids, sid.data(), sid.size() * 4, cudaMemcpyHostToDevice, c->stream));
 		VP_CUDA(c, cudaMemcpyAsync(c->d_splat_pos, spos.data(), spos.size() * 4, cudaMemcpyHostToDevice, c->stream));
@@ -871,8 +890,8 @@ extern "C" int vp_rebuild_from_rle(vp_ctx *c, const uint32_t *ids, uint32_t n, c
 		c->launches += 2;
 		VP_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_pipe[0][t], 0));
 		if (s_first[t + 1] > s_first[t]) {
-			VP_CUDA(c, vp_launch_splat(w, c->d_splat_ids + s_first[t], s_first[t + 1] - s_first[t], c->d_results, c->d_splat_pos + s_first[t], c->d_splat_arena, c->d_arena_state + 0, c->stream));
-			c->launches++;
+			VP_CUDA(c, vp_launch_splat(w, c->d_splat_ids + s_first[t], s_first[t + 1] - s_first[t], c->d_results, c->d_splat_pos + s_first[t], c->d_splat_arena, c->d_arena_state + 0, c->d_splat_scratch, c->stream));
+			c->launches += kSplatLaunches;
 		}
 		if (m_first[t + 1] > m_first[t]) {
 			VP_CUDA(c, vp_launch_mesh(w, c->d_mesh_ids + m_first[t], m_first[t + 1] - m_first[t], c->d_results, c->d_mesh_pos + m_first[t], c->d_mesh_arena, c->d_arena_state + 1, c->stream));

@@ -50,6 +50,28 @@ __device__ __forceinline__ uint32_t nz16(uint4 v)
 	return nz4(v.x) | (nz4(v.y) << 4) | (nz4(v.z) << 8) | (nz4(v.w) << 12);
 }
 
+// Bit 7 of each byte = byte != 0 (other bits cleared).
+__device__ __forceinline__ uint32_t nzflags(uint32_t w)
+{
+	return (((w & 0x7f7f7f7fu) + 0x7f7f7f7fu) | w) & 0x80808080u;
+}
+// 16 bytes -> 128 * (16-bit mask) split over two dot-product accumulators: the byte flags (0 / 0x80) are weighted
+// 1,2,4,..,128 by IDP.4A, so the gather runs on the dot-product unit instead of multiply + shift + or chains.
+// Returns 128 * mask(bytes 0..7) + 256 * 128 * mask(bytes 8..15)  (< 2^23).
+__device__ __forceinline__ uint32_t nz16x128(uint4 v)
+{
+	uint32_t a = __dp4a(nzflags(v.x), 0x08040201u, 0u);
+	a = __dp4a(nzflags(v.y), 0x80402010u, a);
+	uint32_t b = __dp4a(nzflags(v.z), 0x08040201u, 0u);
+	b = __dp4a(nzflags(v.w), 0x80402010u, b);
+	return a + (b << 8);
+}
+// L2 prefetch of a byte range (no shared-memory destination, no completion tracking).
+__device__ __forceinline__ void l2_prefetch(const void *gsrc, uint32_t bytes)
+{
+	asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gsrc), "r"(bytes) : "memory");
+}
+
 // OR adjacent bit pairs and pack the 32 results into the low half: out bit k = in bit 2k | in bit 2k+1.
 __device__ __forceinline__ uint64_t pair_or_compress(uint64_t a)
 {

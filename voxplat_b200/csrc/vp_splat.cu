@@ -25,13 +25,32 @@ using namespace vp;
 
 namespace {
 
-constexpr int kConsumerWarps = 8;
-constexpr int kThreads = (kConsumerWarps + 1) * 32;     // + 1 producer warp
-constexpr int kRing = 4;                                // tiles in the TMA ring
+#ifndef VP_CW
+#define VP_CW 8
+#endif
+#ifndef VP_ZS6
+#define VP_ZS6 16
+#endif
+#ifndef VP_PREFETCH
+#define VP_PREFETCH 0
+#endif
+#ifndef VP_EMIT_MINB
+#define VP_EMIT_MINB 6
+#endif
+#ifndef VP_MINB6
+#define VP_MINB6 5
+#endif
+template <int RB> constexpr int consumer_warps() { return RB == 6 ? VP_CW : 8; }      // tuning hook for the 64^3 build
+#ifndef VP_RING6
+#define VP_RING6 4
+#endif
 
 template <int RB> struct Geo {
 	static constexpr int R = 1 << RB;
-	static constexpr int ZS = 16;                        // z slices per CTA
+	static constexpr int CW = consumer_warps<RB>();      // byte->bit consumer warps
+	static constexpr int RING = RB == 6 ? VP_RING6 : 4;  // tiles in the TMA ring
+	static constexpr int THREADS = (CW + 1) * 32;        // + 1 producer warp
+	static constexpr int ZS = RB == 6 ? VP_ZS6 : 16;     // z slices per CTA
 	static constexpr int CL = R / ZS;                    // CTAs per chunk (cluster size)
 	static constexpr int NW = R > 64 ? R / 64 : 1;       // 64-bit words per level-0 row
 	static constexpr int SLICE = R * R;
@@ -60,9 +79,10 @@ template <int RB> struct Geo {
 	__host__ __device__ static constexpr int grp_off(int l) { return l == 0 ? 0 : grp_off(l - 1) + ngroups(l - 1); }
 	static constexpr int NG = grp_off(5);
 	// shared memory carve-up (bytes)
-	static constexpr int RING_BYTES = kRing * TILE;
+	static constexpr int RING_BYTES = RING * TILE;
 	// the level bit arrays are built after the ring is drained, so they live in the same bytes
-	static constexpr int SCRATCH0 = ((RING_BYTES > LV_WORDS * 8 ? RING_BYTES : LV_WORDS * 8) + 127) / 128 * 128;
+	static constexpr int LV_STRIDE = (LV_WORDS + 1) / 2 * 2;            // uint64 words, 16-byte multiple for bulk copies
+	static constexpr int SCRATCH0 = ((RING_BYTES > LV_STRIDE * 8 ? RING_BYTES : LV_STRIDE * 8) + 127) / 128 * 128;
 	static constexpr int HALO_BYTES = 2 * ZS * R;
 	static constexpr int OCC_WORDS = NSL * (R + 1) * NW;
 	static constexpr int OCCX_WORDS = ZS * NW;
@@ -71,22 +91,41 @@ template <int RB> struct Geo {
 	static constexpr int OFF_OCCX = OFF_OCC + OCC_WORDS * 8;
 	static constexpr int OFF_LV = 0;
 	static constexpr int OFF_BARS = OFF_OCCX + OCCX_WORDS * 8;
-	static constexpr int OFF_MISC = OFF_BARS + (2 * kRing + 1) * 8;
+	static constexpr int OFF_MISC = OFF_BARS + (2 * RING + 2) * 8;
 	static constexpr int SMEM = OFF_MISC + 128 + (NG + 1) * 4;
+	// per-slab scratch in global memory between the count and the emit kernel (16-byte multiples for bulk copies)
+	static constexpr int GP_STRIDE = (NG + 1 + 3) / 4 * 4;              // uint32 words
+	// emit kernel: level bit arrays | select table | group prefixes | barrier + scalars
+	static constexpr int E_OFF_LUT = LV_STRIDE * 8;
+	static constexpr int E_OFF_GP = E_OFF_LUT + 2048;
+	static constexpr int E_OFF_MISC = E_OFF_GP + GP_STRIDE * 4;
+	static constexpr int E_SMEM = E_OFF_MISC + 64;
 };
+constexpr int kEmitWarps = 8;
+constexpr int kSlabRec = 16;        // uint32 per slab record: [0..4] counts, [8..12] first splat of the slab's part of level l
 
-struct Misc {                       // small per-CTA scalars in shared memory
-	uint32_t cnt[5];                // this CTA's splat count per level (read by cluster peers)
-	uint32_t wsum[kConsumerWarps + 1];
-	uint32_t base[5];               // first splat of this CTA's part of level l, relative to the chunk buffer
-	uint32_t total;                 // splats of the whole chunk
-	unsigned long long chunk_off;   // byte offset of the chunk buffer in the arena (~0 = not reserved)
-	uint32_t pad_[2];
+struct Misc {                       // count kernel: small per-CTA area in shared memory
 	uint32_t gpre[1];               // [NG + 1] exclusive prefix of the per-group splat counts (extends past the struct)
 };
-static_assert(offsetof(Misc, gpre) <= 128, "Misc header must fit the reserved 128 bytes");
 
 enum CellKind { MAIN = 0, XPL = 1, YPL = 2, ZPL = 3 };
+
+// kSelLut.v[b * 8 + k] = position of the k-th (0-based) set bit of byte b (8 where b has fewer bits).  Copied to
+// shared memory by one bulk copy per CTA; finishes the rank->bit select of the emission with one LDS.
+struct alignas(16) SelLut {
+	uint8_t v[2048];
+	constexpr SelLut() : v()
+	{
+		for (int b = 0; b < 256; b++)
+			for (int k = 0; k < 8; k++) {
+				int n = 0, pos = 8;
+				for (int i = 0; i < 8; i++)
+					if (b >> i & 1) { if (n == k) { pos = i; break; } n++; }
+				v[b * 8 + k] = (uint8_t)pos;
+			}
+	}
+};
+__device__ const SelLut kSelLut = SelLut();
 
 // Optional phase timing (VP_NVCC_EXTRA=-DVP_PROFILE_PHASES, scripts/phase_probe.py): thread 0 of every CTA
 // accumulates clock64 deltas per phase.  Compiled out by default.
@@ -141,40 +180,22 @@ template <int RB> struct Ctx {
 		}
 	}
 
-	// One splat of level L: int16 x,y,z = origin + (cell << L); int16 colour | shadow << 6, the shadow
-	// sampled at +(1<<L) on every axis for L > 0 (mesher.c:521-531).  (X,Y,Zc) are level-L cell
-	// coordinates in the chunk (the halo index is R>>L); Zloc is the cell's z index inside this CTA's slab.
+	// Colour byte of the level-L cell x of row q (rows in emission order): the voxel found by descending the bit
+	// pyramids to the last non-zero child, one byte gather (L2: this CTA streamed the voxel moments ago).
 	template <int L>
-	__device__ __forceinline__ void emit(unsigned long long *dst, int kind, int X, int Y, int Zloc, int Zc) const
+	__device__ __forceinline__ uint32_t colour(int q, int x) const
 	{
-		const uint32_t wx = ox + ((uint32_t)X << L), wy = oy + ((uint32_t)Y << L), wz = oz + ((uint32_t)Zc << L);
-		constexpr uint32_t d = L ? (1u << L) : 0u;
-		const uint32_t sh = (uint32_t)shadow_pair(w, wx + d, wy + d, wz + d, 1);
-		int cxx = X, cyy = Y, czz = Zloc;
+		constexpr int R = G::R, Rl = G::Rl(L), n_main = G::Zl(L) * (Rl + 1);
+		int kind, cxx = x, cyy, czz;
+		if (q < n_main) { czz = q / (Rl + 1); cyy = q - czz * (Rl + 1); kind = cyy == Rl ? YPL : (x == Rl ? XPL : MAIN); }
+		else { kind = ZPL; cyy = q - n_main; czz = 0; }
 		descend<L>(kind, cxx, cyy, czz);
-		constexpr int R = G::R;
 		const uint8_t *p;
 		if (kind == MAIN) p = own + ((size_t)(z0 + czz) * R + cyy) * R + cxx;
 		else if (kind == XPL) p = nbx_xlo + (size_t)(z0 + czz) * R + cyy;
 		else if (kind == YPL) p = nby + (size_t)(z0 + czz) * R * R + cxx;
 		else p = nbz + (size_t)cyy * R + cxx;
-		const uint32_t col = ((uint32_t)__ldg(p) | (sh << 6)) & 0xFFFFu;
-		const uint32_t lo = (wx & 0xFFFFu) | (wy << 16), hi = (wz & 0xFFFFu) | (col << 16);
-		*reinterpret_cast<uint2 *>(dst) = make_uint2(lo, hi);
-	}
-
-	// Emit list entry `ent` = (row << 8 | x) of level L; q = row index inside the level.
-	template <int L>
-	__device__ __forceinline__ void emit_entry(unsigned long long *dst, int q, int x) const
-	{
-		constexpr int Rl = G::Rl(L), n_main = G::Zl(L) * (Rl + 1);
-		if (q < n_main) {
-			const int Zloc = q / (Rl + 1), Y = q - Zloc * (Rl + 1);
-			const int kind = Y == Rl ? YPL : (x == Rl ? XPL : MAIN);
-			emit<L>(dst, kind, x, Y, Zloc, (z0 >> L) + Zloc);
-		} else {
-			emit<L>(dst, ZPL, x, q - n_main, 0, Rl);
-		}
+		return __ldg(p);
 	}
 };
 
@@ -197,53 +218,146 @@ __device__ __forceinline__ uint64_t load_unit(const uint64_t *lv, int u, uint32_
 	return base[G::zpl_off(L) + (u - n_main * NWl)];
 }
 
-// position of the k-th (0-based) set bit of hi:lo; cl = popc(lo)
-__device__ __forceinline__ int select64(uint32_t lo, uint32_t hi, uint32_t cl, uint32_t k)
+// Position of the k-th (0-based) set bit of hi:lo (k < popc): three popc halving steps down to one byte, then the
+// shared-memory table.  cl = popc(lo).
+__device__ __forceinline__ uint32_t select64(uint32_t lo, uint32_t hi, uint32_t cl, uint32_t k, const uint8_t *lut)
 {
-	uint32_t v = lo, c; int pos = 0;
+	uint32_t v = lo, c, pos = 0;
 	if (k >= cl) { k -= cl; v = hi; pos = 32; }
 	c = __popc(v & 0xFFFFu); if (k >= c) { k -= c; v >>= 16; pos += 16; }
 	c = __popc(v & 0xFFu);   if (k >= c) { k -= c; v >>= 8;  pos += 8; }
-	c = __popc(v & 0xFu);    if (k >= c) { k -= c; v >>= 4;  pos += 4; }
-	c = __popc(v & 0x3u);    if (k >= c) { k -= c; v >>= 2;  pos += 2; }
-	c = v & 1u;              if (k >= c) { pos += 1; }
-	return pos;
+	return pos + lut[(v & 0xFFu) * 8u + (k & 7u)];
 }
 
+// Emission of one group of 32 units of level L by one warp.  Lane i owns unit i: its word, its exclusive splat
+// prefix and a small descriptor of the row the unit lies in (record halves, shadow index, source byte row).
+// Every round the 32 lanes take 32 consecutive output slots; slot s belongs to the unit i with
+// p_i <= s < p_i + c_i (5-step shuffle binary search over the prefixes) and, inside it, to its (s - p_i)-th set
+// bit (select64); the +x plane cell that follows a slab row in scan order is the unit's last slot.  Everything
+// the record needs from the unit comes over shuffles, so a slot costs no divisions and no 64-bit index math.
 template <int RB, int L>
-__device__ __forceinline__ void emit_group(const Ctx<RB> &cx, const uint64_t *lv, int gl, unsigned long long *out_g, int lane)
+__device__ __forceinline__ void emit_group(const Ctx<RB> &cx, const uint64_t *lv, const uint8_t *lut, int gl, uint2 *out_g, int lane)
 {
 	using G = Geo<RB>;
-	constexpr int Rl = G::Rl(L), NWl = G::NWl(L);
+	constexpr int R = G::R, Rl = G::Rl(L), NWl = G::NWl(L), n_main = G::Zl(L) * (Rl + 1);
+	constexpr uint32_t FULL = 0xffffffffu;
+	constexpr uint32_t XW = Rl < 64 ? Rl : 64;           // x of the +x plane cell relative to the unit's first bit
+	constexpr uint32_t d = L ? (1u << L) : 0u;           // shadow sample offset of LOD splats (mesher.c:526-531)
+	const int u = gl * 32 + lane;
 	uint32_t xb;
-	const uint64_t word = load_unit<RB, L>(lv, gl * 32 + lane, xb);
+	const uint64_t word = load_unit<RB, L>(lv, u, xb);
 	const uint32_t lo = (uint32_t)word, hi = (uint32_t)(word >> 32);
-	const uint32_t cl = __popc(lo), cw = cl + __popc(hi), c = cw + xb;
+	const uint32_t c = __popc(lo) + __popc(hi) + xb;
 	uint32_t inc = c;
 	#pragma unroll
-	for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
-	const uint32_t p = inc - c, S = __shfl_sync(0xffffffffu, inc, 31);
+	for (int e = 1; e < 32; e <<= 1) { uint32_t t = __shfl_up_sync(FULL, inc, e); if (lane >= e) inc += t; }
+	const uint32_t p = inc - c, S = __shfl_sync(FULL, inc, 31);
+
+	// unit descriptor
+	const int q = u / NWl, xbase = (u % NWl) * 64;
+	int Y, Zloc; uint32_t Zc;
+	if (q < n_main) { Zloc = q / (Rl + 1); Y = q - Zloc * (Rl + 1); Zc = (uint32_t)((cx.z0 >> L) + Zloc); }
+	else { Zloc = 0; Y = q - n_main; Zc = Rl; }
+	const uint32_t wx0 = cx.ox + ((uint32_t)xbase << L), wy = cx.oy + ((uint32_t)Y << L), wz = cx.oz + (Zc << L);
+	const uint32_t A = (wx0 & 0xFFFFu) | (wy << 16), B = wz & 0xFFFFu;       // world size <= 32768 per axis: wy fits 16 bits
+	const uint32_t shb = (wx0 + d) + (wy + d) + cx.w.sh_w * (wz + d - cx.w.sh_z0);
+	const uint8_t *row = nullptr; uint32_t xo = 0;
+	if constexpr (L == 0) {
+		if (q < n_main) {
+			row = (Y < R ? cx.own + ((size_t)(cx.z0 + Zloc) * R + Y) * R : cx.nby + (size_t)(cx.z0 + Zloc) * R * R) + xbase;
+			xo = (uint32_t)((cx.z0 + Zloc) * R + Y);
+		} else {
+			row = cx.nbz + (size_t)Y * R + xbase;
+		}
+	}
+	const unsigned long long rowa = (unsigned long long)row;
+	const uint32_t rlo = (uint32_t)rowa, rhi = (uint32_t)(rowa >> 32);
+
 	for (uint32_t s0 = 0; s0 < S; s0 += 32) {
 		const uint32_t s = min(s0 + (uint32_t)lane, S - 1);
 		int i = 0;
 		#pragma unroll
-		for (int d = 16; d >= 1; d >>= 1) { const uint32_t pj = __shfl_sync(0xffffffffu, p, i | d); if (pj <= s) i |= d; }
-		const uint32_t pi = __shfl_sync(0xffffffffu, p, i), wlo = __shfl_sync(0xffffffffu, lo, i), whi = __shfl_sync(0xffffffffu, hi, i);
-		const uint32_t wcl = __shfl_sync(0xffffffffu, cl, i), wcw = __shfl_sync(0xffffffffu, cw, i);
-		const uint32_t k = s - pi;
-		const int u = gl * 32 + i, q = u / NWl;
-		const int x = k == wcw ? Rl : select64(wlo, whi, wcl, k) + 64 * (u % NWl);
-		if (s0 + lane < S) cx.template emit_entry<L>(out_g + s0 + lane, q, x);
+		for (int e = 16; e >= 1; e >>= 1) { const uint32_t pj = __shfl_sync(FULL, p, i | e); if (pj <= s) i |= e; }
+		const uint32_t pi = __shfl_sync(FULL, p, i), wlo = __shfl_sync(FULL, lo, i), whi = __shfl_sync(FULL, hi, i);
+		const uint32_t uA = __shfl_sync(FULL, A, i), uB = __shfl_sync(FULL, B, i), ush = __shfl_sync(FULL, shb, i);
+		const uint32_t k = s - pi, wcl = __popc(wlo), wcw = wcl + __popc(whi);
+		const bool isx = k >= wcw;                       // the unit's +x plane cell (only ever its last slot)
+		const uint32_t pos = isx ? XW : select64(wlo, whi, wcl, k, lut);
+		const uint32_t xs = pos << L;
+		// shadow_sample (shadow.h:56-63): !(map[idx] < y+1 && map[idx+1] < y+1)
+		const uint32_t lim = (uA >> 16) + d + 1u;
+		const uint16_t *sp = cx.w.shadow + (ush + xs);
+		const uint32_t sh = (__ldg(sp) >= lim || __ldg(sp + 1) >= lim) ? 64u : 0u;
+		uint32_t col;
+		if constexpr (L == 0) {
+			const uint32_t urlo = __shfl_sync(FULL, rlo, i), urhi = __shfl_sync(FULL, rhi, i), uxo = __shfl_sync(FULL, xo, i);
+			const uint8_t *src = isx ? cx.nbx_xlo + uxo : reinterpret_cast<const uint8_t *>(((unsigned long long)urhi << 32) | urlo) + pos;
+			col = __ldg(src);
+		} else {
+			const int uq = (gl * 32 + i) / NWl;
+			col = cx.template colour<L>(uq, (int)pos + 64 * ((gl * 32 + i) % NWl));
+		}
+		if (s0 + lane < S) {
+			const uint32_t rl = ((uA + xs) & 0xFFFFu) | (uA & 0xFFFF0000u);
+			const uint32_t rh = uB | ((col | sh) << 16);
+			out_g[s0 + lane] = make_uint2(rl, rh);
+		}
 	}
 }
 
+// Scratch between the three kernels of a splat rebuild (device pointers, sized by vp_splat_scratch_bytes).
+struct SplatScratch {
+	uint64_t *pyr;                  // [slabs][LV_STRIDE]  level bit arrays of every non-empty slab
+	uint32_t *gp;                   // [slabs][GP_STRIDE]  exclusive prefix of the per-group splat counts
+	uint32_t *rec;                  // [slabs][kSlabRec]   per-level counts (count kernel) and bases (scan kernel)
+	unsigned long long *choff;      // [chunks]            byte offset of the chunk buffer in the arena (~0 = none)
+};
+
 template <int RB>
-__global__ void __launch_bounds__(kThreads, RB <= 6 ? 5 : 2)
-k_splat(const VpWorldDev w, const uint32_t *__restrict__ ids, VpResultDev *__restrict__ results,
-        const uint32_t *__restrict__ result_pos, uint8_t *__restrict__ arena, VpArenaDev *__restrict__ st)
+__host__ __device__ __forceinline__ SplatScratch carve_scratch(uint8_t *base, uint32_t n)
+{
+	using G = Geo<RB>;
+	const size_t slabs = (size_t)n * G::CL;
+	SplatScratch sc;
+	sc.pyr = reinterpret_cast<uint64_t *>(base);
+	sc.gp = reinterpret_cast<uint32_t *>(base + slabs * G::LV_STRIDE * 8);
+	sc.rec = sc.gp + slabs * G::GP_STRIDE;
+	sc.choff = reinterpret_cast<unsigned long long *>(sc.rec + slabs * kSlabRec);
+	return sc;
+}
+
+// Chunk geometry shared by the count and the emit kernel.
+template <int RB> struct ChunkRefs {
+	int cx, cy, cz;
+	const uint8_t *own, *nbx_xlo, *nby, *nbz;
+	__device__ __forceinline__ ChunkRefs(const VpWorldDev &w, uint32_t cid)
+	{
+		constexpr int R = 1 << RB;
+		cx = (int)(cid & ((1u << w.bits[0]) - 1)); cy = (int)((cid >> w.bits[0]) & ((1u << w.bits[1]) - 1));
+		cz = (int)(cid >> (w.bits[0] + w.bits[1]));
+		const int s_own = chunk_slot(w, cx, cy, cz), s_x = chunk_slot(w, cx + 1, cy, cz);
+		const int s_y = chunk_slot(w, cx, cy + 1, cz), s_z = chunk_slot(w, cx, cy, cz + 1);
+		const size_t N = (size_t)R * R * R;
+		own = s_own >= 0 ? w.vox_pool + (size_t)s_own * N : nullptr;
+		nbx_xlo = s_x >= 0 ? w.xlo_pool + (size_t)s_x * R * R : nullptr;
+		nby = s_y >= 0 ? w.vox_pool + (size_t)s_y * N : nullptr;
+		nbz = s_z >= 0 ? w.vox_pool + (size_t)s_z * N : nullptr;
+	}
+};
+
+// ------------------------------------------------------------------------------------------------------------------
+// Kernel 1: stream one 16-slice slab of a chunk, pack it to bits, derive visibility + LOD bit arrays, count.
+// One CTA per slab, no communication between CTAs: the bit arrays, the group prefixes and the 5 level counts go to
+// the scratch, the scan kernel turns the counts of all slabs into arena offsets, the emit kernel writes the splats.
+// ------------------------------------------------------------------------------------------------------------------
+template <int RB>
+__global__ void __launch_bounds__(Geo<RB>::THREADS, RB <= 6 ? VP_MINB6 : 2)
+k_splat_count(const VpWorldDev w, const uint32_t *__restrict__ ids, uint32_t n, uint8_t *__restrict__ scratch)
 {
 	using G = Geo<RB>;
 	constexpr int R = G::R, ZS = G::ZS, CL = G::CL, NW = G::NW, TILE = G::TILE, TPS = G::TPS, NT = G::NT;
+	constexpr int kConsumerWarps = G::CW, kThreads = G::THREADS, kRing = G::RING;
+	static_assert(kConsumerWarps % kRing == 0 && TILE % (kConsumerWarps / kRing) == 0, "consumer warps must tile the ring slots");
 	extern __shared__ __align__(128) uint8_t smem[];
 	uint8_t *ring = smem;
 	uint8_t *halo = smem + G::OFF_HALO;
@@ -258,28 +372,16 @@ k_splat(const VpWorldDev w, const uint32_t *__restrict__ ids, VpResultDev *__res
 	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 	const int crank = CL > 1 ? (int)(blockIdx.x % CL) : 0;
 	const uint32_t chunk_i = blockIdx.x / CL;
-	const uint32_t cid = ids[chunk_i];
-	const int cx = (int)(cid & ((1u << w.bits[0]) - 1)), cy = (int)((cid >> w.bits[0]) & ((1u << w.bits[1]) - 1));
-	const int cz = (int)(cid >> (w.bits[0] + w.bits[1]));
+	const ChunkRefs<RB> ch(w, ids[chunk_i]);
+	const uint8_t *own = ch.own, *nbx_xlo = ch.nbx_xlo, *nby = ch.nby, *nbz = ch.nbz;
 	const int z0 = crank * ZS;
 	const bool top = (z0 + ZS == R);
-
-	const int s_own = chunk_slot(w, cx, cy, cz), s_x = chunk_slot(w, cx + 1, cy, cz);
-	const int s_y = chunk_slot(w, cx, cy + 1, cz), s_z = chunk_slot(w, cx, cy, cz + 1);
-	const size_t N = (size_t)R * R * R;
-	const uint8_t *own = s_own >= 0 ? w.vox_pool + (size_t)s_own * N : nullptr;
-	const uint8_t *nbx_xlo = s_x >= 0 ? w.xlo_pool + (size_t)s_x * R * R : nullptr;
-	const uint8_t *nby = s_y >= 0 ? w.vox_pool + (size_t)s_y * N : nullptr;
-	const uint8_t *nbz = s_z >= 0 ? w.vox_pool + (size_t)s_z * N : nullptr;
-	VpResultDev *res = results + (result_pos ? result_pos[chunk_i] : chunk_i);
+	const SplatScratch sc = carve_scratch<RB>(scratch, n);
+	uint32_t *rec = sc.rec + (size_t)blockIdx.x * kSlabRec;
 
 	if (!own && !nbx_xlo && !nby && !nbz) {           // mesher.c:404-409: nothing can be visible
-		if (crank == 0 && tid == 0) {
-			res->svl_offset = 0;
-			for (int l = 0; l < 5; l++) res->svl_items[l] = 0;
-			res->svl_items_total = 0;
-		}
-		return;                                        // uniform over the whole cluster
+		if (tid < 5) rec[tid] = 0;
+		return;
 	}
 
 	VP_PHASE_INIT;
@@ -302,10 +404,16 @@ k_splat(const VpWorldDev w, const uint32_t *__restrict__ ids, VpResultDev *__res
 	const bool have_halo = nbx_xlo || nby;
 
 	VP_PHASE(0);
-	// ---- phase 1: TMA producer (warp 8) / byte->bit consumers (warps 0..7) -------------------------
+	// ---- phase 1: TMA producer (last warp) / byte->bit consumers (warps 0..CW-1) -------------------
 	uint32_t any_solid = 0;
 	if (warp == kConsumerWarps) {
 		if (lane == 0) {
+#if VP_PREFETCH
+			for (int sl = kRing / TPS; sl < G::NSL; sl++) {            // slices beyond the first ring fill
+				const uint8_t *src = slice_src(sl);
+				if (src) l2_prefetch(src, R * R);
+			}
+#endif
 			if (have_halo) {
 				mbar_arrive_expect_tx(bar_halo, (nbx_xlo ? ZS * R : 0) + (nby ? ZS * R : 0));
 				if (nbx_xlo) tma_load_1d(halo, nbx_xlo + (size_t)z0 * R, ZS * R, bar_halo);
@@ -324,9 +432,9 @@ k_splat(const VpWorldDev w, const uint32_t *__restrict__ ids, VpResultDev *__res
 			}
 		}
 	} else {
-		// Each ring slot is drained by a FIXED pair of warps (half a tile each), so a warp meets the phases of
-		// its slot strictly in order -- with more consumers than slots a warp could otherwise run two phases
-		// ahead and alias the mbarrier parity.
+		// Each ring slot is drained by a FIXED set of warps (an equal part of the tile each), so a warp meets the
+		// phases of its slot strictly in order -- with more consumers than slots a warp could otherwise run two
+		// phases ahead and alias the mbarrier parity.
 		constexpr int WPS = kConsumerWarps / kRing, PART = TILE / WPS;
 		const int b = warp % kRing, hpart = warp / kRing;
 		for (int t = b; t < NT; t += kRing) {
@@ -335,20 +443,39 @@ k_splat(const VpWorldDev w, const uint32_t *__restrict__ ids, VpResultDev *__res
 			if (slice_src(s)) {
 				const uint8_t *tb = ring + b * TILE;
 				uint64_t *orow = occ + (size_t)(s * (R + 1) + part * G::RPT) * NW;
-				#pragma unroll 4
-				for (int off = hpart * PART + lane * 16; off < (hpart + 1) * PART; off += 512) {
-					const uint4 q4 = *reinterpret_cast<const uint4 *>(tb + off);
-					// all-air shortcut: the occupancy rows are pre-zeroed, so a warp that sees only zeros has nothing to do
-					if (PART >= 512 && !__any_sync(0xffffffffu, (q4.x | q4.y | q4.z | q4.w) != 0u)) continue;
-					const uint32_t m = nz16(q4);
-					any_solid |= m;
-					const int row = off / R, bo = off % R;
-					if (R >= 32) {
-						uint32_t v = m << (bo & 16);
-						v |= __shfl_xor_sync(0xffffffffu, v, 1);
-						if (!(lane & 1)) reinterpret_cast<uint32_t *>(orow + row * NW)[bo >> 5] = v;
-					} else {
-						reinterpret_cast<uint32_t *>(orow + row * NW)[0] = m;
+				if constexpr (PART >= 1024) {
+					// 32 bytes per lane and iteration: two conflict-free 16-byte reads 512 bytes apart.  Lane pairs
+					// exchange their 16-bit masks with one shuffle; the even lane stores the 32-bit word of the first
+					// read, the odd lane the word of the second, so every lane stores once.
+					const uint32_t psel = (lane & 1) ? 0x3276u : 0x5410u;
+					uint32_t *o32 = reinterpret_cast<uint32_t *>(orow);
+					#pragma unroll 2
+					for (int off = hpart * PART + lane * 16; off < (hpart + 1) * PART; off += 1024) {
+						const uint4 qa = *reinterpret_cast<const uint4 *>(tb + off);
+						const uint4 qb = *reinterpret_cast<const uint4 *>(tb + off + 512);
+						// all-air shortcut: the occupancy rows are pre-zeroed
+						if (!__any_sync(0xffffffffu, (qa.x | qa.y | qa.z | qa.w | qb.x | qb.y | qb.z | qb.w) != 0u)) continue;
+						any_solid = 1u;
+						const uint32_t v = __byte_perm(nz16x128(qa) >> 7, nz16x128(qb) >> 7, 0x5410);
+						const uint32_t pv = __shfl_xor_sync(0xffffffffu, v, 1);
+						const int o = (lane & 1) ? off + 512 : off;
+						o32[(o / R) * (R / 32) + ((o % R) >> 5)] = __byte_perm(v, pv, psel);
+					}
+				} else {
+					#pragma unroll 4
+					for (int off = hpart * PART + lane * 16; off < (hpart + 1) * PART; off += 512) {
+						const uint4 q4 = *reinterpret_cast<const uint4 *>(tb + off);
+						if (PART >= 512 && !__any_sync(0xffffffffu, (q4.x | q4.y | q4.z | q4.w) != 0u)) continue;
+						const uint32_t m = nz16(q4);
+						any_solid |= m;
+						const int row = off / R, bo = off % R;
+						if (R >= 32) {
+							uint32_t v = m << (bo & 16);
+							v |= __shfl_xor_sync(0xffffffffu, v, 1);
+							if (!(lane & 1)) reinterpret_cast<uint32_t *>(orow + row * NW)[bo >> 5] = v;
+						} else {
+							reinterpret_cast<uint32_t *>(orow + row * NW)[0] = m;
+						}
 					}
 				}
 			}
@@ -376,15 +503,16 @@ k_splat(const VpWorldDev w, const uint32_t *__restrict__ ids, VpResultDev *__res
 			}
 		}
 	}
-	// A slab without any solid voxel (own, slice above, +x/+y halo) has nothing visible: skip to the exchange.
+	// A slab without any solid voxel (own, slice above, +x/+y halo) has nothing visible.
 	const bool nonempty = __syncthreads_or(any_solid != 0u) != 0;
+	if (!nonempty) {
+		if (tid < 5) rec[tid] = 0;
+		return;
+	}
 	uint64_t *lv0 = lv;
 	uint32_t *gpre = misc->gpre;
-	if (!nonempty) {
-		if (tid < 5) misc->cnt[tid] = 0;
-	} else {
 	VP_PHASE(1);
-	for (int i = tid; i < G::LV_WORDS; i += kThreads) lv[i] = 0;
+	for (int i = tid; i < G::LV_STRIDE; i += kThreads) lv[i] = 0;
 	__syncthreads();
 
 	// ---- phase 2: visibility rows (closed form of the pair walk, mesher.c:421-448) -------------------
@@ -495,118 +623,196 @@ k_splat(const VpWorldDev w, const uint32_t *__restrict__ ids, VpResultDev *__res
 		for (int k = 0; k < IPT; k++) { const int g = lane * IPT + k; if (g < G::NG) gpre[g] = pre; pre += v[k]; }
 		if (lane == 31) gpre[G::NG] = pre;
 		__syncwarp();
-		if (lane < 5) misc->cnt[lane] = gpre[G::grp_off(lane + 1)] - gpre[G::grp_off(lane)];      // grp_off(5) == NG
+		if (lane < 5) rec[lane] = gpre[G::grp_off(lane + 1)] - gpre[G::grp_off(lane)];      // grp_off(5) == NG
 	}
-	}   // nonempty
-
+	__syncthreads();
 	VP_PHASE(4);
-	// ---- phase 5: cluster exchange of the counts, one arena reservation per chunk -------------------
-	if (CL > 1) {
-		cg::cluster_group cluster = cg::this_cluster();
-		cluster.sync();
-		if (tid == 0) {
-			uint32_t tot[5] = {0, 0, 0, 0, 0}, below[5] = {0, 0, 0, 0, 0};
-			for (int r = 0; r < CL; r++) {
-				const Misc *pm = cluster.map_shared_rank(misc, r);
-				for (int l = 0; l < 5; l++) { uint32_t c = pm->cnt[l]; tot[l] += c; if (r < crank) below[l] += c; }
-			}
-			uint32_t acc = 0;
-			for (int l = 0; l < 5; l++) { misc->base[l] = acc + below[l]; acc += tot[l]; }
-			misc->total = acc;
-			if (crank == 0) {
-				unsigned long long bytes = (unsigned long long)acc * 8ull, off = 0;
-				if (acc) {
-					off = atomicAdd(&st->cursor, bytes);
-					if (off + bytes > st->capacity) { atomicExch(&st->overflow, 1u); off = ~0ull; }
-				}
-				for (int r = 0; r < CL; r++) cluster.map_shared_rank(misc, r)->chunk_off = off;
-				res->svl_offset = off;
-				for (int l = 0; l < 5; l++) res->svl_items[l] = tot[l] * 4u;
-				res->svl_items_total = acc * 4u;
-			}
-		}
-		cluster.sync();
-	} else {
-		__syncthreads();
-		if (tid == 0) {
-			uint32_t acc = 0;
-			for (int l = 0; l < 5; l++) { misc->base[l] = acc; acc += misc->cnt[l]; }
-			misc->total = acc;
-			unsigned long long bytes = (unsigned long long)acc * 8ull, off = 0;
-			if (acc) {
-				off = atomicAdd(&st->cursor, bytes);
-				if (off + bytes > st->capacity) { atomicExch(&st->overflow, 1u); off = ~0ull; }
-			}
-			misc->chunk_off = off;
-			res->svl_offset = off;
-			for (int l = 0; l < 5; l++) res->svl_items[l] = misc->cnt[l] * 4u;
-			res->svl_items_total = acc * 4u;
-		}
-		__syncthreads();
+	// ---- phase 5: bit arrays + group prefixes to the scratch (skipped when nothing is visible) -------
+	if (gpre[G::NG] == 0) return;
+	{
+		uint64_t *dp = sc.pyr + (size_t)blockIdx.x * G::LV_STRIDE;
+		for (int i = tid; i < G::LV_STRIDE; i += kThreads) dp[i] = lv[i];
+		uint32_t *dg = sc.gp + (size_t)blockIdx.x * G::GP_STRIDE;
+		for (int i = tid; i < G::NG + 1; i += kThreads) dg[i] = gpre[i];
 	}
 	VP_PHASE(5);
-	if (!nonempty || misc->chunk_off == ~0ull || misc->total == 0) return;
-	unsigned long long *out = reinterpret_cast<unsigned long long *>(arena + misc->chunk_off);
+}
 
-	Ctx<RB> cx_{w, lv, own, nbx_xlo, nby, nbz, z0, (uint32_t)cx << RB, (uint32_t)cy << RB, (uint32_t)cz << RB};
+// ------------------------------------------------------------------------------------------------------------------
+// Kernel 2: one thread per chunk adds up the slab counts, a block scan + one atomicAdd per block reserves the
+// contiguous [L0|L1|L2|L3|L4] buffers of the block's chunks in the arena, the per-slab level bases and the result
+// records (ChunkMD.svl_items[], chunkset.c:469-483) are written.
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_splat_scan(uint32_t n, int CL, uint32_t *__restrict__ rec_all, unsigned long long *__restrict__ choff,
+             VpResultDev *__restrict__ results, const uint32_t *__restrict__ result_pos, VpArenaDev *__restrict__ st)
+{
+	__shared__ unsigned long long wtot[8];
+	__shared__ unsigned long long block_base;
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	uint32_t tot[5] = {0, 0, 0, 0, 0}, acc = 0;
+	if (i < n) {
+		for (int r = 0; r < CL; r++) {
+			const uint32_t *rc = rec_all + ((size_t)i * CL + r) * kSlabRec;
+			#pragma unroll
+			for (int l = 0; l < 5; l++) tot[l] += rc[l];
+		}
+		uint32_t base = 0;
+		#pragma unroll
+		for (int l = 0; l < 5; l++) {
+			uint32_t below = 0;
+			for (int r = 0; r < CL; r++) {
+				uint32_t *rc = rec_all + ((size_t)i * CL + r) * kSlabRec;
+				rc[8 + l] = base + below;
+				below += rc[l];
+			}
+			base += tot[l];
+		}
+		acc = base;
+	}
+	// exclusive block scan of the chunk sizes
+	unsigned long long bytes = (unsigned long long)acc * 8ull, inc = bytes;
+	#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) { unsigned long long t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
+	if (lane == 31) wtot[warp] = inc;
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		unsigned long long run = 0;
+		for (int k = 0; k < 8; k++) { unsigned long long t = wtot[k]; wtot[k] = run; run += t; }
+		unsigned long long off = 0;
+		if (run) {
+			off = atomicAdd(&st->cursor, run);
+			if (off + run > st->capacity) { atomicExch(&st->overflow, 1u); off = ~0ull; }
+		}
+		block_base = off;
+	}
+	__syncthreads();
+	if (i < n) {
+		unsigned long long off = block_base;
+		if (off != ~0ull) off += wtot[warp] + (inc - bytes);
+		if (!acc) off = 0;
+		choff[i] = acc ? off : ~0ull;
+		VpResultDev *res = results + (result_pos ? result_pos[i] : i);
+		res->svl_offset = off;
+		#pragma unroll
+		for (int l = 0; l < 5; l++) res->svl_items[l] = tot[l] * 4u;
+		res->svl_items_total = acc * 4u;
+	}
+}
 
-	// ---- phase 6: emission, one warp per group of 32 units.  Slot s of the group belongs to the unit i
-	// with p_i <= s < p_i + c_i (5-step binary search over the lanes' exclusive prefixes with shuffles),
-	// and inside the unit to its (s - p_i)-th set bit (branch-free popc select).  Every lane emits one
-	// splat per round, so the work is balanced whatever the distribution of visible voxels, and the
-	// 8-byte stores of a warp are contiguous. ---------------------------------------------------------------
-	for (int g = warp; g < G::NG; g += kThreads / 32) {
+// ------------------------------------------------------------------------------------------------------------------
+// Kernel 3: emission.  One CTA per slab fetches the slab's bit arrays, group prefixes and the select table with bulk
+// copies; its warps take groups of 32 units dynamically.  No big shared buffers, so the SM holds many more warps than
+// in a fused kernel: the emission is a chain of shuffles and gathers and needs them to hide its latency.
+// ------------------------------------------------------------------------------------------------------------------
+struct EmitMisc { uint64_t bar; uint32_t next; uint32_t pad; };
+
+template <int RB>
+__global__ void __launch_bounds__(kEmitWarps * 32, VP_EMIT_MINB)
+k_splat_emit(const VpWorldDev w, const uint32_t *__restrict__ ids, uint32_t n, const uint8_t *__restrict__ scratch,
+             uint8_t *__restrict__ arena)
+{
+	using G = Geo<RB>;
+	constexpr int R = G::R, ZS = G::ZS, CL = G::CL;
+	extern __shared__ __align__(128) uint8_t smem[];
+	uint64_t *lv = reinterpret_cast<uint64_t *>(smem);
+	uint8_t *lut = smem + G::E_OFF_LUT;
+	uint32_t *gpre = reinterpret_cast<uint32_t *>(smem + G::E_OFF_GP);
+	EmitMisc *misc = reinterpret_cast<EmitMisc *>(smem + G::E_OFF_MISC);
+
+	const int tid = threadIdx.x, lane = tid & 31;
+	const uint32_t slab = gridDim.x - 1 - blockIdx.x;        // last written first: the tail of the scratch is still in L2
+	const uint32_t chunk_i = slab / CL;
+	const int crank = CL > 1 ? (int)(slab % CL) : 0;
+	const SplatScratch sc = carve_scratch<RB>(const_cast<uint8_t *>(scratch), n);
+	const uint32_t *rec = sc.rec + (size_t)slab * kSlabRec;
+	const uint32_t c0 = rec[0], c1 = rec[1], c2 = rec[2], c3 = rec[3], c4 = rec[4];
+	if ((c0 | c1 | c2 | c3 | c4) == 0) return;
+	const unsigned long long choff = sc.choff[chunk_i];
+	if (choff == ~0ull) return;                               // arena overflow: nothing was reserved
+	if (tid == 0) {
+		mbar_init(&misc->bar, 1);
+		mbar_fence_init();
+		misc->next = 0;
+		mbar_arrive_expect_tx(&misc->bar, G::LV_STRIDE * 8 + 2048 + G::GP_STRIDE * 4);
+		tma_load_1d(lv, sc.pyr + (size_t)slab * G::LV_STRIDE, G::LV_STRIDE * 8, &misc->bar);
+		tma_load_1d(lut, kSelLut.v, 2048, &misc->bar);
+		tma_load_1d(gpre, sc.gp + (size_t)slab * G::GP_STRIDE, G::GP_STRIDE * 4, &misc->bar);
+	}
+	const ChunkRefs<RB> ch(w, ids[chunk_i]);
+	const int z0 = crank * ZS;
+	const uint32_t b0 = rec[8], b1 = rec[9], b2 = rec[10], b3 = rec[11], b4 = rec[12];
+	Ctx<RB> cx_{w, lv, ch.own, ch.nbx_xlo, ch.nby, ch.nbz, z0, (uint32_t)ch.cx << RB, (uint32_t)ch.cy << RB, (uint32_t)ch.cz << RB};
+	uint2 *out2 = reinterpret_cast<uint2 *>(arena + choff);
+	__syncthreads();
+	mbar_wait(&misc->bar, 0);
+
+	// Slot s of a group belongs to the unit i with p_i <= s < p_i + c_i (shuffle binary search over the lanes'
+	// exclusive prefixes) and inside the unit to its (s - p_i)-th set bit (popc select): every lane emits one splat
+	// per round whatever the distribution of visible voxels, and the 8-byte stores of a warp are contiguous.
+	for (;;) {
+		int g = 0;
+		if (lane == 0) g = (int)atomicAdd(&misc->next, 1u);
+		g = __shfl_sync(0xffffffffu, g, 0);
+		if (g >= G::NG) break;
 		const uint32_t gs = gpre[g];
 		if (gpre[g + 1] == gs) continue;
-		if (g < G::grp_off(1)) emit_group<RB, 0>(cx_, lv, g, out + misc->base[0] + (gs - gpre[0]), lane);
-		else if (g < G::grp_off(2)) emit_group<RB, 1>(cx_, lv, g - G::grp_off(1), out + misc->base[1] + (gs - gpre[G::grp_off(1)]), lane);
-		else if (g < G::grp_off(3)) emit_group<RB, 2>(cx_, lv, g - G::grp_off(2), out + misc->base[2] + (gs - gpre[G::grp_off(2)]), lane);
-		else if (g < G::grp_off(4)) emit_group<RB, 3>(cx_, lv, g - G::grp_off(3), out + misc->base[3] + (gs - gpre[G::grp_off(3)]), lane);
-		else emit_group<RB, 4>(cx_, lv, g - G::grp_off(4), out + misc->base[4] + (gs - gpre[G::grp_off(4)]), lane);
+		if (g < G::grp_off(1)) emit_group<RB, 0>(cx_, lv, lut, g, out2 + b0 + (gs - gpre[0]), lane);
+		else if (g < G::grp_off(2)) emit_group<RB, 1>(cx_, lv, lut, g - G::grp_off(1), out2 + b1 + (gs - gpre[G::grp_off(1)]), lane);
+		else if (g < G::grp_off(3)) emit_group<RB, 2>(cx_, lv, lut, g - G::grp_off(2), out2 + b2 + (gs - gpre[G::grp_off(2)]), lane);
+		else if (g < G::grp_off(4)) emit_group<RB, 3>(cx_, lv, lut, g - G::grp_off(3), out2 + b3 + (gs - gpre[G::grp_off(3)]), lane);
+		else emit_group<RB, 4>(cx_, lv, lut, g - G::grp_off(4), out2 + b4 + (gs - gpre[G::grp_off(4)]), lane);
 	}
-#ifdef VP_PROFILE_PHASES
-	__syncthreads();
-	VP_PHASE(6);
-#endif
 }
 
 template <int RB>
 cudaError_t launch(const VpWorldDev &w, const uint32_t *d_ids, uint32_t n, VpResultDev *d_results,
-                   const uint32_t *d_result_pos, uint8_t *arena, VpArenaDev *state, cudaStream_t s)
+                   const uint32_t *d_result_pos, uint8_t *arena, VpArenaDev *state, uint8_t *scratch, cudaStream_t s)
 {
 	using G = Geo<RB>;
 	static bool configured = false;
 	if (!configured) {
-		cudaError_t e = cudaFuncSetAttribute(k_splat<RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM);
+		cudaError_t e = cudaFuncSetAttribute(k_splat_count<RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM);
+		if (e != cudaSuccess) return e;
+		e = cudaFuncSetAttribute(k_splat_emit<RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::E_SMEM);
 		if (e != cudaSuccess) return e;
 		configured = true;
 	}
-	cudaLaunchConfig_t cfg = {};
-	cfg.gridDim = dim3(n * G::CL);
-	cfg.blockDim = dim3(kThreads);
-	cfg.dynamicSmemBytes = G::SMEM;
-	cfg.stream = s;
-	cudaLaunchAttribute attr[1];
-	attr[0].id = cudaLaunchAttributeClusterDimension;
-	attr[0].val.clusterDim.x = G::CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-	cfg.attrs = attr;
-	cfg.numAttrs = G::CL > 1 ? 1 : 0;
-	return cudaLaunchKernelEx(&cfg, k_splat<RB>, w, d_ids, d_results, d_result_pos, arena, state);
+	k_splat_count<RB><<<n * G::CL, G::THREADS, G::SMEM, s>>>(w, d_ids, n, scratch);
+	const SplatScratch sc = carve_scratch<RB>(scratch, n);
+	k_splat_scan<<<(n + 255) / 256, 256, 0, s>>>(n, G::CL, sc.rec, sc.choff, d_results, d_result_pos, state);
+	k_splat_emit<RB><<<n * G::CL, kEmitWarps * 32, G::E_SMEM, s>>>(w, d_ids, n, scratch, arena);
+	return cudaGetLastError();
+}
+
+template <int RB> size_t scratch_bytes(uint32_t n)
+{
+	using G = Geo<RB>;
+	const size_t slabs = (size_t)n * G::CL;
+	return slabs * ((size_t)G::LV_STRIDE * 8 + (size_t)G::GP_STRIDE * 4 + kSlabRec * 4) + (size_t)n * 8 + 256;
 }
 
 } // namespace
 
 cudaError_t vp_launch_splat(const VpWorldDev &w, const uint32_t *d_ids, uint32_t n, VpResultDev *d_results,
-                            const uint32_t *d_result_pos, uint8_t *arena, VpArenaDev *state, cudaStream_t s)
+                            const uint32_t *d_result_pos, uint8_t *arena, VpArenaDev *state, uint8_t *scratch, cudaStream_t s)
 {
 	if (n == 0) return cudaSuccess;
 	switch (w.rb) {
-	case 4: return launch<4>(w, d_ids, n, d_results, d_result_pos, arena, state, s);
-	case 5: return launch<5>(w, d_ids, n, d_results, d_result_pos, arena, state, s);
-	case 6: return launch<6>(w, d_ids, n, d_results, d_result_pos, arena, state, s);
-	case 7: return launch<7>(w, d_ids, n, d_results, d_result_pos, arena, state, s);
+	case 4: return launch<4>(w, d_ids, n, d_results, d_result_pos, arena, state, scratch, s);
+	case 5: return launch<5>(w, d_ids, n, d_results, d_result_pos, arena, state, scratch, s);
+	case 6: return launch<6>(w, d_ids, n, d_results, d_result_pos, arena, state, scratch, s);
+	case 7: return launch<7>(w, d_ids, n, d_results, d_result_pos, arena, state, scratch, s);
 	default: return cudaErrorInvalidValue;
 	}
+}
+
+// Bytes of device scratch a splat rebuild of n chunks needs (bit arrays + prefixes + records of every slab).
+size_t vp_splat_scratch_bytes(int rb, uint32_t n)
+{
+	switch (rb) { case 4: return scratch_bytes<4>(n); case 5: return scratch_bytes<5>(n); case 6: return scratch_bytes<6>(n); case 7: return scratch_bytes<7>(n); }
+	return 0;
 }
 
 int vp_splat_smem_bytes(int rb)
