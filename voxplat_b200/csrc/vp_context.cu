@@ -364,12 +364,13 @@ static int batch_reserve(vp_ctx *c, uint32_t n)
 // Scratch between the count / scan / emit kernels of a splat rebuild of up to n chunks per launch.
 static int splat_scratch_reserve(vp_ctx *c, uint32_t n)
 {
-	const size_t need = vp_splat_scratch_bytes(c->rb, n);
-	if (need <= c->splat_scratch_cap) return VP_OK;
+	if (n <= c->splat_scratch_chunks) return VP_OK;
 	VP_CUDA(c, cudaStreamSynchronize(c->stream));
-	cudaFree(c->d_splat_scratch); c->d_splat_scratch = nullptr; c->splat_scratch_cap = 0;
-	VP_CUDA(c, cudaMalloc(&c->d_splat_scratch, need));
-	c->splat_scratch_cap = need;
+	cudaFree(c->d_splat_scratch); c->d_splat_scratch = nullptr; c->splat_scratch_chunks = 0;
+	const uint32_t cap = std::max<uint32_t>(n + n / 8, 64);
+	VP_CUDA(c, cudaMalloc(&c->d_splat_scratch, vp_splat_scratch_bytes(c->rb, cap)));
+	VP_CUDA(c, cudaMemsetAsync(c->d_splat_scratch, 0, (size_t)cap * 4 + 256, c->stream));      // per-chunk arrival counters start at zero
+	c->splat_scratch_chunks = cap;
 	return VP_OK;
 }
 
@@ -431,7 +432,7 @@ extern "C" int vp_rebuild_device(vp_ctx *c)
 	c->rebuilds++;
 	if (c->n_splat) {
 		VP_CUDA(c, cudaEventRecord(ev[0], c->stream));
-		VP_CUDA(c, vp_launch_splat(w, c->d_splat_ids, c->n_splat, c->d_results, c->d_splat_pos, c->d_splat_arena, c->d_arena_state + 0, c->d_splat_scratch, c->stream));
+		VP_CUDA(c, vp_launch_splat(w, c->d_splat_ids, c->n_splat, c->d_results, c->d_splat_pos, c->d_splat_arena, c->d_arena_state + 0, c->d_splat_scratch, c->splat_scratch_chunks, c->stream));
 		VP_CUDA(c, cudaEventRecord(ev[1], c->stream));
 		valid |= 1;
 		c->launches += kSplatLaunches;
@@ -890,7 +891,7 @@ extern "C" int vp_rebuild_from_rle(vp_ctx *c, const uint32_t *ids, uint32_t n, c
 		c->launches += 2;
 		VP_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_pipe[0][t], 0));
 		if (s_first[t + 1] > s_first[t]) {
-			VP_CUDA(c, vp_launch_splat(w, c->d_splat_ids + s_first[t], s_first[t + 1] - s_first[t], c->d_results, c->d_splat_pos + s_first[t], c->d_splat_arena, c->d_arena_state + 0, c->d_splat_scratch, c->stream));
+			VP_CUDA(c, vp_launch_splat(w, c->d_splat_ids + s_first[t], s_first[t + 1] - s_first[t], c->d_results, c->d_splat_pos + s_first[t], c->d_splat_arena, c->d_arena_state + 0, c->d_splat_scratch, c->splat_scratch_chunks, c->stream));
 			c->launches += kSplatLaunches;
 		}
 		if (m_first[t + 1] > m_first[t]) {

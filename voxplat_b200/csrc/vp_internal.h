@@ -92,7 +92,7 @@ struct vp_ctx {
 	uint8_t *h_io_stage; size_t io_stage_cap;            // pinned staging for uploads / rle
 	uint8_t *d_node_arena; size_t node_arena_cap; VpNodeDev *d_nodes; uint32_t nodes_cap;   // LOD-node aggregation (vp_nodes.cu)
 	uint8_t *h_node_stage; size_t node_stage_cap;
-	uint8_t *d_splat_scratch; size_t splat_scratch_cap;  // bit arrays / counts between the splat kernels
+	uint8_t *d_splat_scratch; uint32_t splat_scratch_chunks;  // bit arrays / counts between the splat kernels
 	uint8_t *d_io; size_t d_io_cap;                      // device scratch for the flat RLE codec / stream offsets
 	uint64_t launches;
 	std::string err;
@@ -103,11 +103,12 @@ int vp_fail(vp_ctx *c, int code, const char *what, cudaError_t e = cudaSuccess);
 #define VP_CUDA(ctx, call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return vp_fail(ctx, VP_ERR_CUDA, #call, e__); } while (0)
 
 // kernel launchers (each returns a cudaError_t from the launch)
-// splat rebuild = 3 launches (count, scan, emit); scratch must hold vp_splat_scratch_bytes(rb, n) bytes
-cudaError_t vp_launch_splat(const VpWorldDev &w, const uint32_t *d_ids, uint32_t n, VpResultDev *d_results,
-                            const uint32_t *d_result_pos, uint8_t *arena, VpArenaDev *state, uint8_t *scratch, cudaStream_t s);
+// splat rebuild = 2 launches (count + reserve, emit); scratch was allocated (and zero-filled once) for launches of up to
+// scratch_chunks chunks: vp_splat_scratch_bytes(rb, scratch_chunks) bytes
+cudaError_t vp_launch_splat(const VpWorldDev &w, const uint32_t *d_ids, uint32_t n, VpResultDev *d_results, const uint32_t *d_result_pos,
+                            uint8_t *arena, VpArenaDev *state, uint8_t *scratch, uint32_t scratch_chunks, cudaStream_t s);
 size_t vp_splat_scratch_bytes(int rb, uint32_t n);
-constexpr int kSplatLaunches = 3;
+constexpr int kSplatLaunches = 2;
 cudaError_t vp_launch_mesh(const VpWorldDev &w, const uint32_t *d_ids, uint32_t n, VpResultDev *d_results,
                            const uint32_t *d_result_pos, uint8_t *arena, VpArenaDev *state, cudaStream_t s);
 cudaError_t vp_launch_extract_xfaces(int rb, const uint8_t *vox_pool, uint8_t *xlo_pool, uint8_t *xhi_pool,

@@ -35,7 +35,7 @@ namespace {
 #define VP_PREFETCH 0
 #endif
 #ifndef VP_EMIT_MINB
-#define VP_EMIT_MINB 6
+#define VP_EMIT_MINB 8
 #endif
 #ifndef VP_MINB6
 #define VP_MINB6 5
@@ -157,12 +157,14 @@ template <int RB> struct Ctx {
 			constexpr int c = K - 1, Rc = G::Rl(c), NWc = G::NWl(c);
 			const uint64_t *cm = lv + G::lvl_off(c);
 			if (kind == MAIN) {
-				uint32_t p = pair_at(cm + ((2 * Z + 1) * (Rc + 1) + 2 * Y + 1) * NWc, 2 * X);
-				int dz = 1, dy = 1;
-				if (!p) { p = pair_at(cm + ((2 * Z + 1) * (Rc + 1) + 2 * Y) * NWc, 2 * X); dy = 0; }
-				if (!p) { p = pair_at(cm + ((2 * Z) * (Rc + 1) + 2 * Y + 1) * NWc, 2 * X); dz = 0; dy = 1; }
-				if (!p) { p = pair_at(cm + ((2 * Z) * (Rc + 1) + 2 * Y) * NWc, 2 * X); dy = 0; }
-				Z = 2 * Z + dz; Y = 2 * Y + dy; X = 2 * X + (int)(p >> 1);
+				// the four child rows' bit pairs, packed in scan order (dz, dy, dx): the highest set bit is the last
+				// non-zero child -- four independent loads instead of a chain of tests
+				const uint64_t *r0 = cm + ((2 * Z) * (Rc + 1) + 2 * Y) * NWc;
+				const int wsel = (2 * X) >> 6, sft = (2 * X) & 63;
+				const uint32_t p00 = (uint32_t)(r0[wsel] >> sft) & 3u, p01 = (uint32_t)(r0[NWc + wsel] >> sft) & 3u;
+				const uint32_t p10 = (uint32_t)(r0[(Rc + 1) * NWc + wsel] >> sft) & 3u, p11 = (uint32_t)(r0[(Rc + 2) * NWc + wsel] >> sft) & 3u;
+				const int top = 31 - __clz((int)(p00 | (p01 << 2) | (p10 << 4) | (p11 << 6)));
+				Z = 2 * Z + (top >> 2); Y = 2 * Y + ((top >> 1) & 1); X = 2 * X + (top & 1);
 			} else if (kind == XPL) {
 				uint32_t p = pair_at(cm + G::xpl_off(c) + (2 * Z + 1) * NWc, 2 * Y);
 				if (p) { Z = 2 * Z + 1; } else { p = pair_at(cm + G::xpl_off(c) + (2 * Z) * NWc, 2 * Y); Z = 2 * Z; }
@@ -272,6 +274,7 @@ __device__ __forceinline__ void emit_group(const Ctx<RB> &cx, const uint64_t *lv
 	}
 	const unsigned long long rowa = (unsigned long long)row;
 	const uint32_t rlo = (uint32_t)rowa, rhi = (uint32_t)(rowa >> 32);
+	const uint32_t Bx = B | (xo << 16);                  // xo < R*R + R <= 16512: both halves fit 16 bits
 
 	for (uint32_t s0 = 0; s0 < S; s0 += 32) {
 		const uint32_t s = min(s0 + (uint32_t)lane, S - 1);
@@ -279,7 +282,7 @@ __device__ __forceinline__ void emit_group(const Ctx<RB> &cx, const uint64_t *lv
 		#pragma unroll
 		for (int e = 16; e >= 1; e >>= 1) { const uint32_t pj = __shfl_sync(FULL, p, i | e); if (pj <= s) i |= e; }
 		const uint32_t pi = __shfl_sync(FULL, p, i), wlo = __shfl_sync(FULL, lo, i), whi = __shfl_sync(FULL, hi, i);
-		const uint32_t uA = __shfl_sync(FULL, A, i), uB = __shfl_sync(FULL, B, i), ush = __shfl_sync(FULL, shb, i);
+		const uint32_t uA = __shfl_sync(FULL, A, i), uB = __shfl_sync(FULL, Bx, i), ush = __shfl_sync(FULL, shb, i);
 		const uint32_t k = s - pi, wcl = __popc(wlo), wcw = wcl + __popc(whi);
 		const bool isx = k >= wcw;                       // the unit's +x plane cell (only ever its last slot)
 		const uint32_t pos = isx ? XW : select64(wlo, whi, wcl, k, lut);
@@ -287,11 +290,12 @@ __device__ __forceinline__ void emit_group(const Ctx<RB> &cx, const uint64_t *lv
 		// shadow_sample (shadow.h:56-63): !(map[idx] < y+1 && map[idx+1] < y+1)
 		const uint32_t lim = (uA >> 16) + d + 1u;
 		const uint16_t *sp = cx.w.shadow + (ush + xs);
-		const uint32_t sh = (__ldg(sp) >= lim || __ldg(sp + 1) >= lim) ? 64u : 0u;
+		const uint32_t sa = __ldg(sp), sb = __ldg(sp + 1);        // both loads in flight together
+		const uint32_t sh = ((sa >= lim) | (sb >= lim)) ? 64u : 0u;
 		uint32_t col;
 		if constexpr (L == 0) {
-			const uint32_t urlo = __shfl_sync(FULL, rlo, i), urhi = __shfl_sync(FULL, rhi, i), uxo = __shfl_sync(FULL, xo, i);
-			const uint8_t *src = isx ? cx.nbx_xlo + uxo : reinterpret_cast<const uint8_t *>(((unsigned long long)urhi << 32) | urlo) + pos;
+			const uint32_t urlo = __shfl_sync(FULL, rlo, i), urhi = __shfl_sync(FULL, rhi, i);
+			const uint8_t *src = isx ? cx.nbx_xlo + (uB >> 16) : reinterpret_cast<const uint8_t *>(((unsigned long long)urhi << 32) | urlo) + pos;
 			col = __ldg(src);
 		} else {
 			const int uq = (gl * 32 + i) / NWl;
@@ -299,14 +303,15 @@ __device__ __forceinline__ void emit_group(const Ctx<RB> &cx, const uint64_t *lv
 		}
 		if (s0 + lane < S) {
 			const uint32_t rl = ((uA + xs) & 0xFFFFu) | (uA & 0xFFFF0000u);
-			const uint32_t rh = uB | ((col | sh) << 16);
+			const uint32_t rh = __byte_perm(uB, col | sh, 0x5410);       // wz | (colour | shadow) << 16
 			out_g[s0 + lane] = make_uint2(rl, rh);
 		}
 	}
 }
 
-// Scratch between the three kernels of a splat rebuild (device pointers, sized by vp_splat_scratch_bytes).
+// Scratch between the two kernels of a splat rebuild (device pointers, sized by vp_splat_scratch_bytes).
 struct SplatScratch {
+	uint32_t *arrived;              // [cap chunks]        slabs of the chunk that finished counting (self-resetting)
 	uint64_t *pyr;                  // [slabs][LV_STRIDE]  level bit arrays of every non-empty slab
 	uint32_t *gp;                   // [slabs][GP_STRIDE]  exclusive prefix of the per-group splat counts
 	uint32_t *rec;                  // [slabs][kSlabRec]   per-level counts (count kernel) and bases (scan kernel)
@@ -314,11 +319,13 @@ struct SplatScratch {
 };
 
 template <int RB>
-__host__ __device__ __forceinline__ SplatScratch carve_scratch(uint8_t *base, uint32_t n)
+__host__ __device__ __forceinline__ SplatScratch carve_scratch(uint8_t *base, size_t arrived_bytes, uint32_t n)
 {
 	using G = Geo<RB>;
 	const size_t slabs = (size_t)n * G::CL;
 	SplatScratch sc;
+	sc.arrived = reinterpret_cast<uint32_t *>(base);                    // fixed position whatever n: stays zero between launches
+	base += arrived_bytes;
 	sc.pyr = reinterpret_cast<uint64_t *>(base);
 	sc.gp = reinterpret_cast<uint32_t *>(base + slabs * G::LV_STRIDE * 8);
 	sc.rec = sc.gp + slabs * G::GP_STRIDE;
@@ -345,6 +352,64 @@ template <int RB> struct ChunkRefs {
 	}
 };
 
+// End of a slab's count pass: the LAST slab of a chunk to get here (per-chunk arrival counter) adds up the level
+// counts of all slabs, reserves the chunk's contiguous [L0|L1|L2|L3|L4] buffer in the arena with one atomicAdd, and
+// writes the per-slab level bases and the result record (ChunkMD.svl_items[], chunkset.c:469-483).  Nobody waits.
+template <int CL>
+__device__ __forceinline__ void chunk_reserve(const SplatScratch &sc, uint32_t chunk_i, VpResultDev *res, VpArenaDev *st)
+{
+	__syncthreads();                                   // this slab's record is written
+	if (threadIdx.x >= 32) return;
+	const int lane = threadIdx.x;
+	if (CL > 1) {
+		uint32_t prev = 0;
+		if (lane == 0) { __threadfence(); prev = atomicAdd(sc.arrived + chunk_i, 1u); }
+		prev = __shfl_sync(0xffffffffu, prev, 0);
+		if (prev != CL - 1) return;
+		if (lane == 0) sc.arrived[chunk_i] = 0;        // ready for the next launch
+		__threadfence();
+	}
+	// lane = 8 * (slab within the pass) + level: all records are read at once, sums and prefixes by shuffles
+	uint32_t *rc = sc.rec + (size_t)chunk_i * CL * kSlabRec;
+	const int l = lane & 7, rr = lane >> 3;
+	constexpr int PASSES = (CL + 3) / 4;
+	uint32_t cnt[PASSES], incl[PASSES], tot = 0;
+	#pragma unroll
+	for (int p = 0; p < PASSES; p++) {
+		const int r = p * 4 + rr;
+		cnt[p] = (l < 5 && r < CL) ? __ldcg(rc + r * kSlabRec + l) : 0u;
+		uint32_t x = cnt[p], t;
+		t = __shfl_up_sync(0xffffffffu, x, 8);  if (rr >= 1) x += t;
+		t = __shfl_up_sync(0xffffffffu, x, 16); if (rr >= 2) x += t;
+		incl[p] = tot + x;                             // slabs 0..r of level l
+		tot += __shfl_sync(0xffffffffu, x, 24 + l);    // + this pass's 4 slabs
+	}
+	// exclusive prefix of the level totals over l (lanes of one 8-lane group)
+	uint32_t pre = tot, t;
+	t = __shfl_up_sync(0xffffffffu, pre, 1, 8); if (l >= 1) pre += t;
+	t = __shfl_up_sync(0xffffffffu, pre, 2, 8); if (l >= 2) pre += t;
+	t = __shfl_up_sync(0xffffffffu, pre, 4, 8); if (l >= 4) pre += t;
+	const uint32_t base_l = pre - tot;
+	const uint32_t total = __shfl_sync(0xffffffffu, pre, 4);               // levels 0..4
+	#pragma unroll
+	for (int p = 0; p < PASSES; p++) {
+		const int r = p * 4 + rr;
+		if (l < 5 && r < CL) rc[r * kSlabRec + 8 + l] = base_l + incl[p] - cnt[p];
+	}
+	unsigned long long off = 0;
+	if (lane == 0 && total) {
+		const unsigned long long bytes = (unsigned long long)total * 8ull;
+		off = atomicAdd(&st->cursor, bytes);
+		if (off + bytes > st->capacity) { atomicExch(&st->overflow, 1u); off = ~0ull; }
+	}
+	if (lane == 0) {
+		sc.choff[chunk_i] = total ? off : ~0ull;
+		res->svl_offset = off;
+		res->svl_items_total = total * 4u;
+	}
+	if (lane < 5) res->svl_items[lane] = tot * 4u;
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // Kernel 1: stream one 16-slice slab of a chunk, pack it to bits, derive visibility + LOD bit arrays, count.
 // One CTA per slab, no communication between CTAs: the bit arrays, the group prefixes and the 5 level counts go to
@@ -352,7 +417,8 @@ template <int RB> struct ChunkRefs {
 // ------------------------------------------------------------------------------------------------------------------
 template <int RB>
 __global__ void __launch_bounds__(Geo<RB>::THREADS, RB <= 6 ? VP_MINB6 : 2)
-k_splat_count(const VpWorldDev w, const uint32_t *__restrict__ ids, uint32_t n, uint8_t *__restrict__ scratch)
+k_splat_count(const VpWorldDev w, const uint32_t *__restrict__ ids, uint32_t n, uint8_t *__restrict__ scratch, size_t arrived_bytes,
+              VpResultDev *__restrict__ results, const uint32_t *__restrict__ result_pos, VpArenaDev *__restrict__ st)
 {
 	using G = Geo<RB>;
 	constexpr int R = G::R, ZS = G::ZS, CL = G::CL, NW = G::NW, TILE = G::TILE, TPS = G::TPS, NT = G::NT;
@@ -376,11 +442,13 @@ k_splat_count(const VpWorldDev w, const uint32_t *__restrict__ ids, uint32_t n, 
 	const uint8_t *own = ch.own, *nbx_xlo = ch.nbx_xlo, *nby = ch.nby, *nbz = ch.nbz;
 	const int z0 = crank * ZS;
 	const bool top = (z0 + ZS == R);
-	const SplatScratch sc = carve_scratch<RB>(scratch, n);
+	const SplatScratch sc = carve_scratch<RB>(scratch, arrived_bytes, n);
 	uint32_t *rec = sc.rec + (size_t)blockIdx.x * kSlabRec;
 
+	VpResultDev *res = results + (result_pos ? result_pos[chunk_i] : chunk_i);
 	if (!own && !nbx_xlo && !nby && !nbz) {           // mesher.c:404-409: nothing can be visible
 		if (tid < 5) rec[tid] = 0;
+		chunk_reserve<CL>(sc, chunk_i, res, st);
 		return;
 	}
 
@@ -459,7 +527,7 @@ k_splat_count(const VpWorldDev w, const uint32_t *__restrict__ ids, uint32_t n, 
 						const uint32_t v = __byte_perm(nz16x128(qa) >> 7, nz16x128(qb) >> 7, 0x5410);
 						const uint32_t pv = __shfl_xor_sync(0xffffffffu, v, 1);
 						const int o = (lane & 1) ? off + 512 : off;
-						o32[(o / R) * (R / 32) + ((o % R) >> 5)] = __byte_perm(v, pv, psel);
+						o32[o >> 5] = __byte_perm(v, pv, psel);          // rows of a slice are contiguous 32-bit words
 					}
 				} else {
 					#pragma unroll 4
@@ -507,6 +575,7 @@ k_splat_count(const VpWorldDev w, const uint32_t *__restrict__ ids, uint32_t n, 
 	const bool nonempty = __syncthreads_or(any_solid != 0u) != 0;
 	if (!nonempty) {
 		if (tid < 5) rec[tid] = 0;
+		chunk_reserve<CL>(sc, chunk_i, res, st);
 		return;
 	}
 	uint64_t *lv0 = lv;
@@ -628,81 +697,18 @@ k_splat_count(const VpWorldDev w, const uint32_t *__restrict__ ids, uint32_t n, 
 	__syncthreads();
 	VP_PHASE(4);
 	// ---- phase 5: bit arrays + group prefixes to the scratch (skipped when nothing is visible) -------
-	if (gpre[G::NG] == 0) return;
-	{
+	if (gpre[G::NG] != 0) {
 		uint64_t *dp = sc.pyr + (size_t)blockIdx.x * G::LV_STRIDE;
 		for (int i = tid; i < G::LV_STRIDE; i += kThreads) dp[i] = lv[i];
 		uint32_t *dg = sc.gp + (size_t)blockIdx.x * G::GP_STRIDE;
 		for (int i = tid; i < G::NG + 1; i += kThreads) dg[i] = gpre[i];
 	}
+	chunk_reserve<CL>(sc, chunk_i, res, st);
 	VP_PHASE(5);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// Kernel 2: one thread per chunk adds up the slab counts, a block scan + one atomicAdd per block reserves the
-// contiguous [L0|L1|L2|L3|L4] buffers of the block's chunks in the arena, the per-slab level bases and the result
-// records (ChunkMD.svl_items[], chunkset.c:469-483) are written.
-// ------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-k_splat_scan(uint32_t n, int CL, uint32_t *__restrict__ rec_all, unsigned long long *__restrict__ choff,
-             VpResultDev *__restrict__ results, const uint32_t *__restrict__ result_pos, VpArenaDev *__restrict__ st)
-{
-	__shared__ unsigned long long wtot[8];
-	__shared__ unsigned long long block_base;
-	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	uint32_t tot[5] = {0, 0, 0, 0, 0}, acc = 0;
-	if (i < n) {
-		for (int r = 0; r < CL; r++) {
-			const uint32_t *rc = rec_all + ((size_t)i * CL + r) * kSlabRec;
-			#pragma unroll
-			for (int l = 0; l < 5; l++) tot[l] += rc[l];
-		}
-		uint32_t base = 0;
-		#pragma unroll
-		for (int l = 0; l < 5; l++) {
-			uint32_t below = 0;
-			for (int r = 0; r < CL; r++) {
-				uint32_t *rc = rec_all + ((size_t)i * CL + r) * kSlabRec;
-				rc[8 + l] = base + below;
-				below += rc[l];
-			}
-			base += tot[l];
-		}
-		acc = base;
-	}
-	// exclusive block scan of the chunk sizes
-	unsigned long long bytes = (unsigned long long)acc * 8ull, inc = bytes;
-	#pragma unroll
-	for (int d = 1; d < 32; d <<= 1) { unsigned long long t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
-	if (lane == 31) wtot[warp] = inc;
-	__syncthreads();
-	if (threadIdx.x == 0) {
-		unsigned long long run = 0;
-		for (int k = 0; k < 8; k++) { unsigned long long t = wtot[k]; wtot[k] = run; run += t; }
-		unsigned long long off = 0;
-		if (run) {
-			off = atomicAdd(&st->cursor, run);
-			if (off + run > st->capacity) { atomicExch(&st->overflow, 1u); off = ~0ull; }
-		}
-		block_base = off;
-	}
-	__syncthreads();
-	if (i < n) {
-		unsigned long long off = block_base;
-		if (off != ~0ull) off += wtot[warp] + (inc - bytes);
-		if (!acc) off = 0;
-		choff[i] = acc ? off : ~0ull;
-		VpResultDev *res = results + (result_pos ? result_pos[i] : i);
-		res->svl_offset = off;
-		#pragma unroll
-		for (int l = 0; l < 5; l++) res->svl_items[l] = tot[l] * 4u;
-		res->svl_items_total = acc * 4u;
-	}
-}
-
-// ------------------------------------------------------------------------------------------------------------------
-// Kernel 3: emission.  One CTA per slab fetches the slab's bit arrays, group prefixes and the select table with bulk
+// Kernel 2: emission.  One CTA per slab fetches the slab's bit arrays, group prefixes and the select table with bulk
 // copies; its warps take groups of 32 units dynamically.  No big shared buffers, so the SM holds many more warps than
 // in a fused kernel: the emission is a chain of shuffles and gathers and needs them to hide its latency.
 // ------------------------------------------------------------------------------------------------------------------
@@ -710,7 +716,7 @@ struct EmitMisc { uint64_t bar; uint32_t next; uint32_t pad; };
 
 template <int RB>
 __global__ void __launch_bounds__(kEmitWarps * 32, VP_EMIT_MINB)
-k_splat_emit(const VpWorldDev w, const uint32_t *__restrict__ ids, uint32_t n, const uint8_t *__restrict__ scratch,
+k_splat_emit(const VpWorldDev w, const uint32_t *__restrict__ ids, uint32_t n, const uint8_t *__restrict__ scratch, size_t arrived_bytes,
              uint8_t *__restrict__ arena)
 {
 	using G = Geo<RB>;
@@ -725,7 +731,7 @@ k_splat_emit(const VpWorldDev w, const uint32_t *__restrict__ ids, uint32_t n, c
 	const uint32_t slab = gridDim.x - 1 - blockIdx.x;        // last written first: the tail of the scratch is still in L2
 	const uint32_t chunk_i = slab / CL;
 	const int crank = CL > 1 ? (int)(slab % CL) : 0;
-	const SplatScratch sc = carve_scratch<RB>(const_cast<uint8_t *>(scratch), n);
+	const SplatScratch sc = carve_scratch<RB>(const_cast<uint8_t *>(scratch), arrived_bytes, n);
 	const uint32_t *rec = sc.rec + (size_t)slab * kSlabRec;
 	const uint32_t c0 = rec[0], c1 = rec[1], c2 = rec[2], c3 = rec[3], c4 = rec[4];
 	if ((c0 | c1 | c2 | c3 | c4) == 0) return;
@@ -766,9 +772,12 @@ k_splat_emit(const VpWorldDev w, const uint32_t *__restrict__ ids, uint32_t n, c
 	}
 }
 
+// The per-chunk arrival counters sit at the start of the scratch, sized by the capacity it was allocated for.
+inline size_t arrived_region_bytes(uint32_t cap_chunks) { return ((size_t)cap_chunks * 4 + 255) / 256 * 256; }
+
 template <int RB>
-cudaError_t launch(const VpWorldDev &w, const uint32_t *d_ids, uint32_t n, VpResultDev *d_results,
-                   const uint32_t *d_result_pos, uint8_t *arena, VpArenaDev *state, uint8_t *scratch, cudaStream_t s)
+cudaError_t launch(const VpWorldDev &w, const uint32_t *d_ids, uint32_t n, VpResultDev *d_results, const uint32_t *d_result_pos,
+                   uint8_t *arena, VpArenaDev *state, uint8_t *scratch, uint32_t scratch_chunks, cudaStream_t s)
 {
 	using G = Geo<RB>;
 	static bool configured = false;
@@ -779,10 +788,9 @@ cudaError_t launch(const VpWorldDev &w, const uint32_t *d_ids, uint32_t n, VpRes
 		if (e != cudaSuccess) return e;
 		configured = true;
 	}
-	k_splat_count<RB><<<n * G::CL, G::THREADS, G::SMEM, s>>>(w, d_ids, n, scratch);
-	const SplatScratch sc = carve_scratch<RB>(scratch, n);
-	k_splat_scan<<<(n + 255) / 256, 256, 0, s>>>(n, G::CL, sc.rec, sc.choff, d_results, d_result_pos, state);
-	k_splat_emit<RB><<<n * G::CL, kEmitWarps * 32, G::E_SMEM, s>>>(w, d_ids, n, scratch, arena);
+	const size_t arrived_bytes = arrived_region_bytes(scratch_chunks);
+	k_splat_count<RB><<<n * G::CL, G::THREADS, G::SMEM, s>>>(w, d_ids, n, scratch, arrived_bytes, d_results, d_result_pos, state);
+	k_splat_emit<RB><<<n * G::CL, kEmitWarps * 32, G::E_SMEM, s>>>(w, d_ids, n, scratch, arrived_bytes, arena);
 	return cudaGetLastError();
 }
 
@@ -790,25 +798,27 @@ template <int RB> size_t scratch_bytes(uint32_t n)
 {
 	using G = Geo<RB>;
 	const size_t slabs = (size_t)n * G::CL;
-	return slabs * ((size_t)G::LV_STRIDE * 8 + (size_t)G::GP_STRIDE * 4 + kSlabRec * 4) + (size_t)n * 8 + 256;
+	return arrived_region_bytes(n) + slabs * ((size_t)G::LV_STRIDE * 8 + (size_t)G::GP_STRIDE * 4 + kSlabRec * 4) + (size_t)n * 8 + 256;
 }
 
 } // namespace
 
-cudaError_t vp_launch_splat(const VpWorldDev &w, const uint32_t *d_ids, uint32_t n, VpResultDev *d_results,
-                            const uint32_t *d_result_pos, uint8_t *arena, VpArenaDev *state, uint8_t *scratch, cudaStream_t s)
+cudaError_t vp_launch_splat(const VpWorldDev &w, const uint32_t *d_ids, uint32_t n, VpResultDev *d_results, const uint32_t *d_result_pos,
+                            uint8_t *arena, VpArenaDev *state, uint8_t *scratch, uint32_t scratch_chunks, cudaStream_t s)
 {
 	if (n == 0) return cudaSuccess;
+	if (n > scratch_chunks) return cudaErrorInvalidValue;
 	switch (w.rb) {
-	case 4: return launch<4>(w, d_ids, n, d_results, d_result_pos, arena, state, scratch, s);
-	case 5: return launch<5>(w, d_ids, n, d_results, d_result_pos, arena, state, scratch, s);
-	case 6: return launch<6>(w, d_ids, n, d_results, d_result_pos, arena, state, scratch, s);
-	case 7: return launch<7>(w, d_ids, n, d_results, d_result_pos, arena, state, scratch, s);
+	case 4: return launch<4>(w, d_ids, n, d_results, d_result_pos, arena, state, scratch, scratch_chunks, s);
+	case 5: return launch<5>(w, d_ids, n, d_results, d_result_pos, arena, state, scratch, scratch_chunks, s);
+	case 6: return launch<6>(w, d_ids, n, d_results, d_result_pos, arena, state, scratch, scratch_chunks, s);
+	case 7: return launch<7>(w, d_ids, n, d_results, d_result_pos, arena, state, scratch, scratch_chunks, s);
 	default: return cudaErrorInvalidValue;
 	}
 }
 
-// Bytes of device scratch a splat rebuild of n chunks needs (bit arrays + prefixes + records of every slab).
+// Bytes of device scratch for splat rebuilds of up to n chunks per launch (arrival counters, which must be zero
+// before the first launch, then bit arrays + prefixes + records of every slab).
 size_t vp_splat_scratch_bytes(int rb, uint32_t n)
 {
 	switch (rb) { case 4: return scratch_bytes<4>(n); case 5: return scratch_bytes<5>(n); case 6: return scratch_bytes<6>(n); case 7: return scratch_bytes<7>(n); }
