@@ -95,6 +95,9 @@ static void ctx_free(vp_ctx *c)
 	cudaFreeHost(c->h_io_stage);
 	if (c->own_stream) cudaStreamDestroy(c->own_stream);
 	if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+	if (c->mesh_stream) cudaStreamDestroy(c->mesh_stream);
+	if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+	if (c->ev_join) cudaEventDestroy(c->ev_join);
 	if (c->down_stream) cudaStreamDestroy(c->down_stream);
 	for (int k = 0; k < 2; k++) for (int i = 0; i < 64; i++) if (c->ev_pipe[k][i]) cudaEventDestroy(c->ev_pipe[k][i]);
 	cudaFreeHost(c->h_steps);
@@ -138,6 +141,9 @@ extern "C" int vp_ctx_create(const vp_config *cfg, vp_ctx **out)
 	CK(cudaSetDevice(cfg->device));
 	CK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
 	CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+	CK(cudaStreamCreateWithFlags(&c->mesh_stream, cudaStreamNonBlocking));
+	CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+	CK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
 	CK(cudaStreamCreateWithFlags(&c->down_stream, cudaStreamNonBlocking));
 	for (int k = 0; k < 2; k++) for (int i = 0; i < 64; i++) CK(cudaEventCreateWithFlags(&c->ev_pipe[k][i], cudaEventDisableTiming));
 	CK(cudaHostAlloc(&c->h_steps, 64 * 2 * sizeof(VpArenaDev), cudaHostAllocDefault));
@@ -430,6 +436,21 @@ extern "C" int vp_rebuild_device(vp_ctx *c)
 	uint8_t &valid = c->ev_k_valid[c->rebuilds % vp_ctx::kHist];
 	valid = 0;
 	c->rebuilds++;
+	// The mesh kernel (few chunks, latency bound) runs on its own stream beside the splat kernels: the two write
+	// disjoint fields of the result records and separate arenas.
+	const bool fork = c->n_splat && c->n_mesh;
+	cudaStream_t ms = fork ? c->mesh_stream : c->stream;
+	if (fork) {
+		VP_CUDA(c, cudaEventRecord(c->ev_fork, c->stream));
+		VP_CUDA(c, cudaStreamWaitEvent(ms, c->ev_fork, 0));
+	}
+	if (c->n_mesh) {
+		VP_CUDA(c, cudaEventRecord(ev[2], ms));
+		VP_CUDA(c, vp_launch_mesh(w, c->d_mesh_ids, c->n_mesh, c->d_results, c->d_mesh_pos, c->d_mesh_arena, c->d_arena_state + 1, ms));
+		VP_CUDA(c, cudaEventRecord(ev[3], ms));
+		valid |= 2;
+		c->launches++;
+	}
 	if (c->n_splat) {
 		VP_CUDA(c, cudaEventRecord(ev[0], c->stream));
 		VP_CUDA(c, vp_launch_splat(w, c->d_splat_ids, c->n_splat, c->d_results, c->d_splat_pos, c->d_splat_arena, c->d_arena_state + 0, c->d_splat_scratch, c->splat_scratch_chunks, c->stream));
@@ -437,12 +458,9 @@ extern "C" int vp_rebuild_device(vp_ctx *c)
 		valid |= 1;
 		c->launches += kSplatLaunches;
 	}
-	if (c->n_mesh) {
-		VP_CUDA(c, cudaEventRecord(ev[2], c->stream));
-		VP_CUDA(c, vp_launch_mesh(w, c->d_mesh_ids, c->n_mesh, c->d_results, c->d_mesh_pos, c->d_mesh_arena, c->d_arena_state + 1, c->stream));
-		VP_CUDA(c, cudaEventRecord(ev[3], c->stream));
-		valid |= 2;
-		c->launches++;
+	if (fork) {
+		VP_CUDA(c, cudaEventRecord(c->ev_join, ms));
+		VP_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_join, 0));
 	}
 	return VP_OK;
 }

@@ -63,6 +63,8 @@ struct vp_ctx {
 	uint32_t n_ext;               // chunks in the extended slab
 	cudaStream_t own_stream, stream;
 	cudaStream_t copy_stream, down_stream;
+	cudaStream_t mesh_stream;     // the mesh kernel of a rebuild runs beside the splat kernels
+	cudaEvent_t ev_fork, ev_join;
 	cudaEvent_t ev_pipe[2][64];   // [0] decode done, [1] kernels done, per pipeline step
 	VpArenaDev *h_steps;          // pinned: arena states after every pipeline step [64][2]
 	uint64_t last_splat_bytes, last_mesh_bytes;

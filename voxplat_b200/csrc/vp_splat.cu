@@ -26,19 +26,19 @@ using namespace vp;
 namespace {
 
 #ifndef VP_CW
-#define VP_CW 8
+#define VP_CW 4
 #endif
 #ifndef VP_ZS6
 #define VP_ZS6 16
 #endif
 #ifndef VP_PREFETCH
-#define VP_PREFETCH 0
+#define VP_PREFETCH 1
 #endif
 #ifndef VP_EMIT_MINB
 #define VP_EMIT_MINB 8
 #endif
 #ifndef VP_MINB6
-#define VP_MINB6 5
+#define VP_MINB6 8
 #endif
 template <int RB> constexpr int consumer_warps() { return RB == 6 ? VP_CW : 8; }      // tuning hook for the 64^3 build
 #ifndef VP_RING6
@@ -92,9 +92,11 @@ template <int RB> struct Geo {
 	static constexpr int OFF_LV = 0;
 	static constexpr int OFF_BARS = OFF_OCCX + OCCX_WORDS * 8;
 	static constexpr int OFF_MISC = OFF_BARS + (2 * RING + 2) * 8;
-	static constexpr int SMEM = OFF_MISC + 128 + (NG + 1) * 4;
+	// group record: [NG + 1] exclusive splat prefix, [1] number of non-empty groups, [NG bytes] their indices
+	static constexpr int GP_WORDS = NG + 2 + (NG + 3) / 4;
+	static constexpr int SMEM = OFF_MISC + GP_WORDS * 4 + 16;
 	// per-slab scratch in global memory between the count and the emit kernel (16-byte multiples for bulk copies)
-	static constexpr int GP_STRIDE = (NG + 1 + 3) / 4 * 4;              // uint32 words
+	static constexpr int GP_STRIDE = (GP_WORDS + 3) / 4 * 4;            // uint32 words
 	// emit kernel: level bit arrays | select table | group prefixes | barrier + scalars
 	static constexpr int E_OFF_LUT = LV_STRIDE * 8;
 	static constexpr int E_OFF_GP = E_OFF_LUT + 2048;
@@ -416,7 +418,7 @@ __device__ __forceinline__ void chunk_reserve(const SplatScratch &sc, uint32_t c
 // the scratch, the scan kernel turns the counts of all slabs into arena offsets, the emit kernel writes the splats.
 // ------------------------------------------------------------------------------------------------------------------
 template <int RB>
-__global__ void __launch_bounds__(Geo<RB>::THREADS, RB <= 6 ? VP_MINB6 : 2)
+__global__ void __launch_bounds__(Geo<RB>::THREADS, RB == 6 ? VP_MINB6 : (RB < 6 ? 5 : 2))
 k_splat_count(const VpWorldDev w, const uint32_t *__restrict__ ids, uint32_t n, uint8_t *__restrict__ scratch, size_t arrived_bytes,
               VpResultDev *__restrict__ results, const uint32_t *__restrict__ result_pos, VpArenaDev *__restrict__ st)
 {
@@ -693,6 +695,18 @@ k_splat_count(const VpWorldDev w, const uint32_t *__restrict__ ids, uint32_t n, 
 		if (lane == 31) gpre[G::NG] = pre;
 		__syncwarp();
 		if (lane < 5) rec[lane] = gpre[G::grp_off(lane + 1)] - gpre[G::grp_off(lane)];      // grp_off(5) == NG
+		// list of the non-empty groups: the emit kernel's warps take entries of this list, not all NG groups
+		static_assert(G::NG <= 255, "group indices are stored as bytes");
+		uint8_t *glist = reinterpret_cast<uint8_t *>(gpre + G::NG + 2);
+		uint32_t nne = 0;
+		for (int g0 = 0; g0 < G::NG; g0 += 32) {
+			const int g = g0 + lane;
+			const bool ne = g < G::NG && gpre[g + 1] != gpre[g];
+			const uint32_t m = __ballot_sync(0xffffffffu, ne);
+			if (ne) glist[nne + __popc(m & ((1u << lane) - 1u))] = (uint8_t)g;
+			nne += __popc(m);
+		}
+		if (lane == 0) gpre[G::NG + 1] = nne;
 	}
 	__syncthreads();
 	VP_PHASE(4);
@@ -701,7 +715,7 @@ k_splat_count(const VpWorldDev w, const uint32_t *__restrict__ ids, uint32_t n, 
 		uint64_t *dp = sc.pyr + (size_t)blockIdx.x * G::LV_STRIDE;
 		for (int i = tid; i < G::LV_STRIDE; i += kThreads) dp[i] = lv[i];
 		uint32_t *dg = sc.gp + (size_t)blockIdx.x * G::GP_STRIDE;
-		for (int i = tid; i < G::NG + 1; i += kThreads) dg[i] = gpre[i];
+		for (int i = tid; i < G::GP_WORDS; i += kThreads) dg[i] = gpre[i];
 	}
 	chunk_reserve<CL>(sc, chunk_i, res, st);
 	VP_PHASE(5);
@@ -757,13 +771,15 @@ k_splat_emit(const VpWorldDev w, const uint32_t *__restrict__ ids, uint32_t n, c
 	// Slot s of a group belongs to the unit i with p_i <= s < p_i + c_i (shuffle binary search over the lanes'
 	// exclusive prefixes) and inside the unit to its (s - p_i)-th set bit (popc select): every lane emits one splat
 	// per round whatever the distribution of visible voxels, and the 8-byte stores of a warp are contiguous.
+	const uint32_t nne = gpre[G::NG + 1];
+	const uint8_t *glist = reinterpret_cast<const uint8_t *>(gpre + G::NG + 2);
 	for (;;) {
-		int g = 0;
-		if (lane == 0) g = (int)atomicAdd(&misc->next, 1u);
-		g = __shfl_sync(0xffffffffu, g, 0);
-		if (g >= G::NG) break;
+		uint32_t k = 0;
+		if (lane == 0) k = atomicAdd(&misc->next, 1u);
+		k = __shfl_sync(0xffffffffu, k, 0);
+		if (k >= nne) break;
+		const int g = glist[k];
 		const uint32_t gs = gpre[g];
-		if (gpre[g + 1] == gs) continue;
 		if (g < G::grp_off(1)) emit_group<RB, 0>(cx_, lv, lut, g, out2 + b0 + (gs - gpre[0]), lane);
 		else if (g < G::grp_off(2)) emit_group<RB, 1>(cx_, lv, lut, g - G::grp_off(1), out2 + b1 + (gs - gpre[G::grp_off(1)]), lane);
 		else if (g < G::grp_off(3)) emit_group<RB, 2>(cx_, lv, lut, g - G::grp_off(2), out2 + b2 + (gs - gpre[G::grp_off(2)]), lane);
