@@ -160,19 +160,38 @@ def reference_world(bits):
     return w, (lambda ids, mode, nt: ow.rebuild(ids, mode, nt)[0]), "port"
 
 
+class stdout_to_stderr:
+    """The compiled reference logs to stdout (log.c via printf); keep stdout for the ONE JSON line."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def __exit__(self, *exc):
+        try:
+            import ctypes
+            ctypes.CDLL(None).fflush(None)          # the C library's buffered lines belong to stderr too
+        except Exception:
+            pass
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
 def cpu_rebuild_seconds(bits, sample_chunks=None):
     """One full (or sampled) rebuild with every host thread: splat path on all sampled chunks + mesh path
     on the near-camera ones.  Returns (seconds, voxels, cores, kind, sample description)."""
     from voxplat_b200 import slab
-    w, rebuild, kind = reference_world(bits)
-    ids = np.arange(w.n_chunks, dtype=np.uint32)
-    if sample_chunks and sample_chunks < len(ids):
-        ids = ids[:sample_chunks]
-    near = ids[slab.near_camera_flags(ids, ROOT_BITW, bits)]
-    cores = os.cpu_count() or 1
-    t = rebuild(ids, 0, cores)
-    if len(near):
-        t += rebuild(near, 1, cores)
+    with stdout_to_stderr():
+        w, rebuild, kind = reference_world(bits)
+        ids = np.arange(w.n_chunks, dtype=np.uint32)
+        if sample_chunks and sample_chunks < len(ids):
+            ids = ids[:sample_chunks]
+        near = ids[slab.near_camera_flags(ids, ROOT_BITW, bits)]
+        cores = os.cpu_count() or 1
+        t = rebuild(ids, 0, cores)
+        if len(near):
+            t += rebuild(near, 1, cores)
     desc = "%d of %d chunks (%s), splat all + mesh %d near, %d threads, OpenMP dynamic" % (
         len(ids), w.n_chunks, "whole world" if len(ids) == w.n_chunks else "first chunk rows", len(near), cores)
     return t, len(ids) * w.N, cores, kind, desc
@@ -188,16 +207,17 @@ def run_reference(args):
     # bounded sample: one GPU's share of the workload = the N = 1 world (CPU throughput does not depend on the
     # world's z extent), so the run ends within minutes and needs ~1 GB of host memory
     sample_bits = world_bits(1)
-    w, rebuild, kind = reference_world(sample_bits)
-    n_sample = w.n_chunks
-    ids = np.arange(n_sample, dtype=np.uint32)
-    near = ids[slab.near_camera_flags(ids, ROOT_BITW, sample_bits)]
-    cores = os.cpu_count() or 1
-    times = []
-    for i in range(args.warmup + args.steps):
-        t = rebuild(ids, 0, cores) + (rebuild(near, 1, cores) if len(near) else 0.0)
-        if i >= args.warmup:
-            times.append(t)
+    with stdout_to_stderr():
+        w, rebuild, kind = reference_world(sample_bits)
+        n_sample = w.n_chunks
+        ids = np.arange(n_sample, dtype=np.uint32)
+        near = ids[slab.near_camera_flags(ids, ROOT_BITW, sample_bits)]
+        cores = os.cpu_count() or 1
+        times = []
+        for i in range(args.warmup + args.steps):
+            t = rebuild(ids, 0, cores) + (rebuild(near, 1, cores) if len(near) else 0.0)
+            if i >= args.warmup:
+                times.append(t)
     sec = float(np.mean(times))
     gv = n_sample * w.N / sec / 1e9
     desc = "%d chunks per step = the 2048x256x2048 world (one GPU's share; splat all + mesh %d near), %d host threads, OpenMP dynamic schedule" % (
@@ -285,6 +305,14 @@ def run_native(args):
         launches = ctx.kernel_launches() - launches0
         hist_n = min(args.steps, 256)
         splat_ms, mesh_ms = ctx.kernel_ms_history(hist_n)
+        # the splat kernels alone (the timed step runs the mesh kernel beside them on a second stream)
+        ctx.batch_prepare(own_ids, flags=vpb.VP_REBUILD_SPLAT)
+        iso_n = max(3, min(args.steps, 20))
+        for _ in range(iso_n):
+            ctx.rebuild_device()
+        barrier()
+        splat_iso_ms, _ = ctx.kernel_ms_history(iso_n)
+        ctx.batch_prepare(own_ids, per_chunk_flags=flags)
 
         # ---- end to end through the host-facing C ABI: host RLE streams -> H2D -> decode -> rebuild -> D2H ----
         words, offs = ctx.encode_chunks_rle(own_ids[nn])
@@ -357,9 +385,13 @@ def run_native(args):
                        "parallelism": "z-slabs of %d chunk rows per GPU, NCCL border planes" % (nz // world_size) if world_size > 1 else "single GPU",
                        "l2": "inputs larger than L2 (%.2f GB of voxels per GPU, no flush needed)" % (len(nn) * N / 1e9),
                        "splats": int(agg[2].item()), "mesh_faces": int(agg[3].item())},
-            "roofline": {"bound": "hbm", "kernel": "k_splat (cull + 5 LOD + splat emission), rank 0", "achieved": achieved, "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": "k_splat_count + k_splat_emit (cull + 5 LOD, then splat emission; timed as one pair), rank 0",
+                         "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": sb_a, "kernel_ms": k_ms,
+                         "kernel_ms_alone": float(np.mean(splat_iso_ms)), "frac_alone": sb_a / (float(np.mean(splat_iso_ms)) * 1e-3) / 1e9 / peak,
+                         "step": {"algorithmic_bytes": sb_a + mb_a, "achieved": (sb_a + mb_a) / (total_ms / args.steps * 1e-3) / 1e9,
+                                  "frac": (sb_a + mb_a) / (total_ms / args.steps * 1e-3) / 1e9 / peak},
                          "mesh_kernel": {"kernel_ms": float(np.mean(mesh_ms)), "algorithmic_bytes_per_launch": mb_a,
                                          "achieved": mb_a / max(float(np.mean(mesh_ms)), 1e-9) / 1e6}},
             "e2e": {"value": e2e_value, "unit": "Gvoxel/s", "h2d_bytes_per_step": int(agg[4].item()), "d2h_bytes_per_step": int(agg[5].item()),

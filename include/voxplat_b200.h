@@ -44,7 +44,8 @@ typedef enum {
 	VP_ERR_CUDA       = -3,             /* a CUDA runtime call failed */
 	VP_ERR_ARENA_FULL = -4,             /* output arena too small; counts are valid, grow and retry */
 	VP_ERR_RLE        = -5,             /* malformed RLE stream (length != chunk volume) */
-	VP_ERR_NOT_RESIDENT = -6            /* chunk id outside this context's slab */
+	VP_ERR_NOT_RESIDENT = -6,           /* chunk id outside this context's slab */
+	VP_ERR_IO         = -7              /* world file missing, truncated or not a VOXPLAT file */
 } vp_status;
 
 /* Rebuild flags: which of the dispatcher's two branches to run (chunkset.c:337 `if (c->make_mesh)`). */
@@ -214,6 +215,18 @@ typedef struct {
  * kernel_ms (optional) receives the device time of the gather. */
 VP_API int  vp_build_lod_nodes(vp_ctx *ctx, uint32_t lod, vp_node_result *nodes, uint32_t cap_nodes, uint32_t *n_nodes,
                         const void **base, float *kernel_ms);
+
+/* ---- world file: checkpoint / resume ------------------------------------------------ */
+
+/* The layout of the reference's exporter command_export (src/deadcode.c:320-350): byte 0x89 + "VOXPLAT", root_bitw
+ * (1 byte), max_bitw (3 bytes), every chunk's RLE stream in chunk-id order (rle_compress words with their 0
+ * terminator, rle.c:44-87; null chunks as the all-air stream {R^3, 0}, chunkset.c:98), then the whole shadow map,
+ * (X+Y)*Z uint16 (shadow.h:26-51).  Streams are encoded / decoded on the device.  The context must hold the whole
+ * world (slab = all chunk rows).  vp_world_load requires a context created with the file's root_bitw / max_bitw
+ * (vp_world_file_info reads them without a device). */
+VP_API int  vp_world_save(vp_ctx *ctx, const char *path, uint64_t *bytes_written);
+VP_API int  vp_world_load(vp_ctx *ctx, const char *path);
+VP_API int  vp_world_file_info(const char *path, int32_t *root_bitw, int32_t max_bitw[3], uint64_t *file_bytes);
 
 /* ---- multi-GPU slab borders (new: the reference is single-process) ----------------------------- */
 

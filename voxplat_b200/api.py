@@ -42,6 +42,16 @@ NODE_DTYPE = np.dtype([("offset", "<u8"), ("items", "<u4"), ("members", "<u4")])
 _lib = None
 
 
+def world_file_info(path):
+    """(root_bitw, max_bitw, file_bytes) of a world file; needs no device."""
+    lib = load_library()
+    rb, mb, nb = C.c_int32(), (C.c_int32 * 3)(), C.c_uint64()
+    rc = lib.vp_world_file_info(os.fsencode(path), C.byref(rb), C.byref(mb), C.byref(nb))
+    if rc != VP_OK:
+        raise RuntimeError("voxplat_b200: %s is not a VOXPLAT world file (error %d)" % (path, rc))
+    return int(rb.value), tuple(int(x) for x in mb), int(nb.value)
+
+
 def load_library():
     """Load the CUDA C-ABI library; raises if it has not been built (python -m voxplat_b200.build)."""
     global _lib
@@ -83,6 +93,9 @@ def load_library():
         "vp_edit_sphere": (C.c_int, [vp, C.c_int32, C.c_int32, C.c_int32, C.c_uint32, C.c_uint8, vp, C.c_uint32, C.POINTER(C.c_uint32)]),
         "vp_download_shadow_rows": (C.c_int, [vp, C.c_uint32, C.c_uint32, vp]),
         "vp_build_lod_nodes": (C.c_int, [vp, C.c_uint32, vp, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(vp), C.POINTER(C.c_float)]),
+        "vp_world_save": (C.c_int, [vp, C.c_char_p, C.POINTER(C.c_uint64)]),
+        "vp_world_load": (C.c_int, [vp, C.c_char_p]),
+        "vp_world_file_info": (C.c_int, [C.c_char_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32 * 3), C.POINTER(C.c_uint64)]),
         "vp_halo_plane_bytes": (C.c_uint64, [vp]),
         "vp_halo_pack": (C.c_int, [vp, C.c_int, vp]),
         "vp_halo_unpack": (C.c_int, [vp, C.c_int, vp]),
@@ -188,6 +201,17 @@ class Context:
                 continue
             self._ck(rc)
             return words[:int(offs[-1])], offs
+
+    # ---- world file: checkpoint / resume (deadcode.c:320-350 layout) -------------------------------------
+    def save_world(self, path):
+        """Write the resident world (device RLE encode of every chunk + shadow map); returns the file size."""
+        n = C.c_uint64()
+        self._ck(self.lib.vp_world_save(self.h, os.fsencode(path), C.byref(n)))
+        return int(n.value)
+
+    def load_world(self, path):
+        """Replace the resident world by the file's (device RLE decode); geometry must match the context's."""
+        self._ck(self.lib.vp_world_load(self.h, os.fsencode(path)))
 
     def upload_shadow_rows(self, z0, rows):
         rows = np.ascontiguousarray(rows, dtype=np.uint16)
