@@ -216,6 +216,16 @@ typedef struct {
 VP_API int  vp_build_lod_nodes(vp_ctx *ctx, uint32_t lod, vp_node_result *nodes, uint32_t cap_nodes, uint32_t *n_nodes,
                         const void **base, float *kernel_ms);
 
+/* ---- world generation on the device ------------------------------------------------- */
+
+/* Fill the context's slab with the deterministic synthetic world of seed `seed` without any host -> device voxel
+ * traffic: terrain + trees of the integer generator (csrc/vp_worldgen_core.h: the structure of chunkset/gen.c:89-184,
+ * 305-323 with a pinned integer noise; gen.c's own arithmetic lives in the un-vendored FastNoise), all-air chunks become
+ * null chunks (chunkset.c:225-228), and the height map is built on the device by the shadow_place_update rule
+ * (shadow.h:77-89) in a fixed order.  Same resident state as vp_upload_chunks_dense + vp_upload_shadow_rows of the host
+ * generator (libvpworldgen.so), byte for byte.  Worlds taller than 1024 voxels: VP_ERR_ARG. */
+VP_API int  vp_generate_world(vp_ctx *ctx, uint32_t seed);
+
 /* ---- world file: checkpoint / resume ------------------------------------------------ */
 
 /* The layout of the reference's exporter command_export (src/deadcode.c:320-350): byte 0x89 + "VOXPLAT", root_bitw

@@ -93,6 +93,7 @@ def load_library():
         "vp_edit_sphere": (C.c_int, [vp, C.c_int32, C.c_int32, C.c_int32, C.c_uint32, C.c_uint8, vp, C.c_uint32, C.POINTER(C.c_uint32)]),
         "vp_download_shadow_rows": (C.c_int, [vp, C.c_uint32, C.c_uint32, vp]),
         "vp_build_lod_nodes": (C.c_int, [vp, C.c_uint32, vp, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(vp), C.POINTER(C.c_float)]),
+        "vp_generate_world": (C.c_int, [vp, C.c_uint32]),
         "vp_world_save": (C.c_int, [vp, C.c_char_p, C.POINTER(C.c_uint64)]),
         "vp_world_load": (C.c_int, [vp, C.c_char_p]),
         "vp_world_file_info": (C.c_int, [C.c_char_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32 * 3), C.POINTER(C.c_uint64)]),
@@ -201,6 +202,10 @@ class Context:
                 continue
             self._ck(rc)
             return words[:int(offs[-1])], offs
+
+    def generate_world(self, seed):
+        """Generate the slab's chunks and height-map rows on the device (same world as worldgen.World(seed, ...))."""
+        self._ck(self.lib.vp_generate_world(self.h, seed))
 
     # ---- world file: checkpoint / resume (deadcode.c:320-350 layout) -------------------------------------
     def save_world(self, path):

@@ -298,6 +298,86 @@ extern "C" int vp_upload_chunks_dense(vp_ctx *c, const uint32_t *ids, uint32_t n
 	return VP_OK;
 }
 
+// World generation on the device: the owned chunk rows are generated batch by batch into a staging
+// buffer (k_gen_chunks), all-air chunks become null chunks exactly like an upload would make them (chunkset.c:225-228),
+// the others are copied to their pool slots; then the height map rows of the slab (+17 rows of reach into the next chunk
+// row, generated transiently) are built from the voxels (k_shadow_rows).  Same resident state as
+// vp_upload_chunks_dense + vp_upload_shadow_rows of the host generator's world (csrc/vp_worldgen.c).
+namespace {
+struct DevBuf {
+	void *p = nullptr;
+	~DevBuf() { if (p) cudaFree(p); }
+	template <class T> T *as() const { return static_cast<T *>(p); }
+};
+}
+
+extern "C" int vp_generate_world(vp_ctx *c, uint32_t seed)
+{
+	if (!c) return VP_ERR_ARG;
+	VP_CUDA(c, cudaSetDevice(c->cfg.device));
+	const size_t N = (size_t)1 << (3 * c->rb);
+	const uint32_t per_row = (uint32_t)c->nx * c->ny;
+	const uint32_t first = (uint32_t)c->cfg.slab_z0 * per_row, count = (uint32_t)(c->cfg.slab_z1 - c->cfg.slab_z0) * per_row;
+	const uint32_t Zw = (uint32_t)c->nz << c->rb, z_own_end = (uint32_t)c->cfg.slab_z1 << c->rb;
+	if (((uint32_t)c->ny << c->rb) > 1024u) return vp_fail(c, VP_ERR_ARG, "vp_generate_world: worlds taller than 1024 voxels are generated on the host");
+	const int bits[3] = {c->cfg.max_bitw[0], c->cfg.max_bitw[1], c->cfg.max_bitw[2]};
+	const uint32_t B = std::max<uint32_t>(per_row, std::min<uint32_t>(count, 1024));       // a whole chunk row fits (reach rows below)
+	DevBuf staging, dids, dsolid, dslots, dtable;
+	VP_CUDA(c, cudaMalloc(&staging.p, (size_t)B * N));
+	VP_CUDA(c, cudaMalloc(&dids.p, (size_t)B * 4));
+	VP_CUDA(c, cudaMalloc(&dsolid.p, (size_t)B * 4));
+	VP_CUDA(c, cudaMalloc(&dslots.p, (size_t)B * 4));
+	std::vector<uint32_t> ids(B), solid(B);
+	std::vector<uint8_t> want(B);
+	std::vector<int32_t> slots;
+	for (uint32_t done = 0; done < count; done += B) {
+		const uint32_t n = std::min(B, count - done);
+		for (uint32_t i = 0; i < n; i++) ids[i] = first + done + i;
+		VP_CUDA(c, cudaMemcpyAsync(dids.p, ids.data(), (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
+		VP_CUDA(c, vp_launch_gen_chunks(seed, c->rb, bits, dids.as<uint32_t>(), n, staging.as<uint8_t>(), dsolid.as<uint32_t>(), c->stream));
+		VP_CUDA(c, cudaMemcpyAsync(solid.data(), dsolid.p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+		VP_CUDA(c, cudaStreamSynchronize(c->stream));
+		for (uint32_t i = 0; i < n; i++) want[i] = solid[i] != 0;
+		int rc = assign_slots(c, ids.data(), n, want.data(), slots);
+		if (rc) return rc;
+		if ((rc = push_slot_table(c, ids.data(), n))) return rc;
+		VP_CUDA(c, cudaMemcpyAsync(dslots.p, slots.data(), (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
+		VP_CUDA(c, vp_launch_scatter_chunks(c->rb, staging.as<uint8_t>(), dslots.as<int32_t>(), n, c->vox_pool, c->stream));
+		VP_CUDA(c, vp_launch_extract_xfaces(c->rb, c->vox_pool, c->xlo_pool, c->xhi_pool, dslots.as<int32_t>(), n, c->stream));
+		c->launches += 3;
+		VP_CUDA(c, cudaStreamSynchronize(c->stream));
+	}
+	// height map: rows of the owned chunk rows from the pool ...
+	const uint32_t shw = (uint32_t)((c->nx + c->ny) << c->rb);
+	std::vector<const uint8_t *> table((size_t)std::max(count, per_row));
+	for (uint32_t i = 0; i < count; i++) {
+		const int32_t s = c->h_slot[(size_t)ext_index(c, first + i)];
+		table[i] = s >= 0 ? c->vox_pool + (size_t)s * N : nullptr;
+	}
+	VP_CUDA(c, cudaMalloc(&dtable.p, table.size() * sizeof(void *)));
+	VP_CUDA(c, cudaMemcpyAsync(dtable.p, table.data(), (size_t)count * sizeof(void *), cudaMemcpyHostToDevice, c->stream));
+	cudaError_t e = vp_launch_shadow_rows(c->rb, dtable.as<const uint8_t *>(), c->nx, c->ny, (uint32_t)c->cfg.slab_z0, c->sh_z0, std::min(c->sh_z1, z_own_end), c->d_shadow, c->stream);
+	if (e != cudaSuccess) return vp_fail(c, VP_ERR_CUDA, "vp_generate_world: shadow rows", e);
+	c->launches++;
+	VP_CUDA(c, cudaStreamSynchronize(c->stream));
+	// ... and the rows of reach past the slab (LOD splats sample up to 16 rows ahead) from the next chunk row, generated transiently
+	if (c->sh_z1 > z_own_end && z_own_end < Zw) {
+		for (uint32_t i = 0; i < per_row; i++) ids[i] = (uint32_t)c->cfg.slab_z1 * per_row + i;
+		VP_CUDA(c, cudaMemcpyAsync(dids.p, ids.data(), (size_t)per_row * 4, cudaMemcpyHostToDevice, c->stream));
+		VP_CUDA(c, vp_launch_gen_chunks(seed, c->rb, bits, dids.as<uint32_t>(), per_row, staging.as<uint8_t>(), dsolid.as<uint32_t>(), c->stream));
+		VP_CUDA(c, cudaMemcpyAsync(solid.data(), dsolid.p, (size_t)per_row * 4, cudaMemcpyDeviceToHost, c->stream));
+		VP_CUDA(c, cudaStreamSynchronize(c->stream));
+		for (uint32_t i = 0; i < per_row; i++) table[i] = solid[i] ? staging.as<uint8_t>() + (size_t)i * N : nullptr;
+		VP_CUDA(c, cudaMemcpyAsync(dtable.p, table.data(), (size_t)per_row * sizeof(void *), cudaMemcpyHostToDevice, c->stream));
+		e = vp_launch_shadow_rows(c->rb, dtable.as<const uint8_t *>(), c->nx, c->ny, (uint32_t)c->cfg.slab_z1, z_own_end, c->sh_z1,
+		                          c->d_shadow + (size_t)(z_own_end - c->sh_z0) * shw, c->stream);
+		if (e != cudaSuccess) return vp_fail(c, VP_ERR_CUDA, "vp_generate_world: shadow rows of reach", e);
+		c->launches += 2;
+		VP_CUDA(c, cudaStreamSynchronize(c->stream));
+	}
+	return VP_OK;
+}
+
 extern "C" int vp_set_chunks_null(vp_ctx *c, const uint32_t *ids, uint32_t n)
 {
 	if (!c || (n && !ids)) return vp_fail(c, VP_ERR_ARG, "vp_set_chunks_null: null argument");

@@ -123,3 +123,8 @@ cudaError_t vp_launch_lod_nodes(int lod, const int bits[3], uint32_t n_nodes, co
                                 uint8_t *d_node_arena, VpArenaDev *state, VpNodeDev *d_nodes, unsigned long long *d_chunk_dst, cudaStream_t s);
 cudaError_t vp_launch_edit_sphere(const VpWorldDev &w, uint8_t *vox_pool, uint16_t *shadow, int cx, int cy, int cz, int radius, int voxel,
                                   int own_z0, int own_z1, cudaStream_t s);
+
+// device world generator (vp_worldgen_dev.cu)
+cudaError_t vp_launch_gen_chunks(uint32_t seed, int rb, const int bits[3], const uint32_t *d_ids, uint32_t n, uint8_t *d_out, uint32_t *d_solid, cudaStream_t s);
+cudaError_t vp_launch_scatter_chunks(int rb, const uint8_t *staging, const int32_t *d_slots, uint32_t n, uint8_t *pool, cudaStream_t s);
+cudaError_t vp_launch_shadow_rows(int rb, const uint8_t *const *table, int nx, int ny, uint32_t row0, uint32_t z0, uint32_t z1, uint16_t *rows_out, cudaStream_t s);
