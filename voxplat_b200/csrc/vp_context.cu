@@ -2,6 +2,9 @@
 // uploads, batch rebuild orchestration, staging.  No CPU compute path exists here: every data
 // transformation is a CUDA kernel (vp_splat.cu, vp_mesh.cu, vp_rle.cu, the small kernels below).
 #include "vp_internal.h"
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <cstdio>
 #include <algorithm>
@@ -322,6 +325,10 @@ extern "C" int vp_generate_world(vp_ctx *c, uint32_t seed)
 	if (((uint32_t)c->ny << c->rb) > 1024u) return vp_fail(c, VP_ERR_ARG, "vp_generate_world: worlds taller than 1024 voxels are generated on the host");
 	const int bits[3] = {c->cfg.max_bitw[0], c->cfg.max_bitw[1], c->cfg.max_bitw[2]};
 	const uint32_t B = std::max<uint32_t>(per_row, std::min<uint32_t>(count, 1024));       // a whole chunk row fits (reach rows below)
+	const bool trace = getenv("VP_TRACE") != nullptr;
+	auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+	double t0 = now();
+	auto lap = [&](const char *what) { if (trace) { cudaStreamSynchronize(c->stream); double t = now(); fprintf(stderr, "[vp_generate_world] %-24s %8.2f ms\n", what, t - t0); t0 = t; } };
 	DevBuf staging, dids, dsolid, dslots, dtable;
 	VP_CUDA(c, cudaMalloc(&staging.p, (size_t)B * N));
 	VP_CUDA(c, cudaMalloc(&dids.p, (size_t)B * 4));
@@ -330,6 +337,7 @@ extern "C" int vp_generate_world(vp_ctx *c, uint32_t seed)
 	std::vector<uint32_t> ids(B), solid(B);
 	std::vector<uint8_t> want(B);
 	std::vector<int32_t> slots;
+	lap("allocations");
 	for (uint32_t done = 0; done < count; done += B) {
 		const uint32_t n = std::min(B, count - done);
 		for (uint32_t i = 0; i < n; i++) ids[i] = first + done + i;
@@ -337,6 +345,7 @@ extern "C" int vp_generate_world(vp_ctx *c, uint32_t seed)
 		VP_CUDA(c, vp_launch_gen_chunks(seed, c->rb, bits, dids.as<uint32_t>(), n, staging.as<uint8_t>(), dsolid.as<uint32_t>(), c->stream));
 		VP_CUDA(c, cudaMemcpyAsync(solid.data(), dsolid.p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
 		VP_CUDA(c, cudaStreamSynchronize(c->stream));
+		lap("k_gen_chunks + flags");
 		for (uint32_t i = 0; i < n; i++) want[i] = solid[i] != 0;
 		int rc = assign_slots(c, ids.data(), n, want.data(), slots);
 		if (rc) return rc;
@@ -346,6 +355,7 @@ extern "C" int vp_generate_world(vp_ctx *c, uint32_t seed)
 		VP_CUDA(c, vp_launch_extract_xfaces(c->rb, c->vox_pool, c->xlo_pool, c->xhi_pool, dslots.as<int32_t>(), n, c->stream));
 		c->launches += 3;
 		VP_CUDA(c, cudaStreamSynchronize(c->stream));
+		lap("slots + scatter + xfaces");
 	}
 	// height map: rows of the owned chunk rows from the pool ...
 	const uint32_t shw = (uint32_t)((c->nx + c->ny) << c->rb);
@@ -360,6 +370,7 @@ extern "C" int vp_generate_world(vp_ctx *c, uint32_t seed)
 	if (e != cudaSuccess) return vp_fail(c, VP_ERR_CUDA, "vp_generate_world: shadow rows", e);
 	c->launches++;
 	VP_CUDA(c, cudaStreamSynchronize(c->stream));
+	lap("k_shadow_rows");
 	// ... and the rows of reach past the slab (LOD splats sample up to 16 rows ahead) from the next chunk row, generated transiently
 	if (c->sh_z1 > z_own_end && z_own_end < Zw) {
 		for (uint32_t i = 0; i < per_row; i++) ids[i] = (uint32_t)c->cfg.slab_z1 * per_row + i;
