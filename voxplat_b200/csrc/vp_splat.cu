@@ -34,6 +34,9 @@ namespace {
 #ifndef VP_PREFETCH
 #define VP_PREFETCH 1
 #endif
+#ifndef VP_EMIT_STATIC
+#define VP_EMIT_STATIC 0
+#endif
 #ifndef VP_EMIT_MINB
 #define VP_EMIT_MINB 8
 #endif
@@ -100,10 +103,12 @@ template <int RB> struct Geo {
 	// emit kernel: level bit arrays | select table | group prefixes | barrier + scalars
 	static constexpr int E_OFF_LUT = LV_STRIDE * 8;
 	static constexpr int E_OFF_GP = E_OFF_LUT + 2048;
-	static constexpr int E_OFF_MISC = E_OFF_GP + GP_STRIDE * 4;
+	static constexpr int E_OFF_STAGE = E_OFF_GP + GP_STRIDE * 4;        // per warp: 2 x 32 uint4 unit descriptors
+	static constexpr int E_OFF_MISC = E_OFF_STAGE + 8 * 64 * 16;
 	static constexpr int E_SMEM = E_OFF_MISC + 64;
 };
-constexpr int kEmitWarps = 8;
+constexpr int kEmitWarps = 8;      // E_OFF_MISC assumes 8 staging areas
+constexpr int kChunkRec = 8;        // uint64 per chunk record
 constexpr int kSlabRec = 16;        // uint32 per slab record: [0..4] counts, [8..12] first splat of the slab's part of level l
 
 struct Misc {                       // count kernel: small per-CTA area in shared memory
@@ -240,7 +245,7 @@ __device__ __forceinline__ uint32_t select64(uint32_t lo, uint32_t hi, uint32_t 
 // bit (select64); the +x plane cell that follows a slab row in scan order is the unit's last slot.  Everything
 // the record needs from the unit comes over shuffles, so a slot costs no divisions and no 64-bit index math.
 template <int RB, int L>
-__device__ __forceinline__ void emit_group(const Ctx<RB> &cx, const uint64_t *lv, const uint8_t *lut, int gl, uint2 *out_g, int lane)
+__device__ __forceinline__ void emit_group(const Ctx<RB> &cx, const uint64_t *lv, const uint8_t *lut, uint4 *stage, int gl, uint2 *out_g, int lane)
 {
 	using G = Geo<RB>;
 	constexpr int R = G::R, Rl = G::Rl(L), NWl = G::NWl(L), n_main = G::Zl(L) * (Rl + 1);
@@ -278,13 +283,27 @@ __device__ __forceinline__ void emit_group(const Ctx<RB> &cx, const uint64_t *lv
 	const uint32_t rlo = (uint32_t)rowa, rhi = (uint32_t)(rowa >> 32);
 	const uint32_t Bx = B | (xo << 16);                  // xo < R*R + R <= 16512: both halves fit 16 bits
 
+	// The non-empty units are compacted into the warp's staging rows (rank = popc of the ballot below the lane): their
+	// prefixes are then strictly increasing, so "which unit owns slot s" is a popc over the mask of unit starts inside
+	// the round's window instead of a shuffle binary search, and the 8 descriptor words come back as two 16-byte reads.
+	const uint32_t ne = __ballot_sync(FULL, c != 0u), n_ne = __popc(ne);
+	const uint32_t rank = __popc(ne & ((1u << lane) - 1u));
+	__syncwarp();                                        // the previous group's readers are done with the staging rows
+	if (c) {
+		stage[rank] = make_uint4(p, lo, hi, A);
+		stage[32 + rank] = make_uint4(Bx, shb, L == 0 ? rlo : (uint32_t)u, rhi);
+	}
+	__syncwarp();
+	const uint32_t pc = (uint32_t)lane < n_ne ? stage[lane].x : 0xFFFFFFFFu;       // start slot of compacted unit `lane`
+
 	for (uint32_t s0 = 0; s0 < S; s0 += 32) {
-		const uint32_t s = min(s0 + (uint32_t)lane, S - 1);
-		int i = 0;
-		#pragma unroll
-		for (int e = 16; e >= 1; e >>= 1) { const uint32_t pj = __shfl_sync(FULL, p, i | e); if (pj <= s) i |= e; }
-		const uint32_t pi = __shfl_sync(FULL, p, i), wlo = __shfl_sync(FULL, lo, i), whi = __shfl_sync(FULL, hi, i);
-		const uint32_t uA = __shfl_sync(FULL, A, i), uB = __shfl_sync(FULL, Bx, i), ush = __shfl_sync(FULL, shb, i);
+		const uint32_t t = min((uint32_t)lane, S - 1 - s0), s = s0 + t;
+		const uint32_t dd = pc - s0;
+		const uint32_t heads = __reduce_or_sync(FULL, dd < 32u ? 1u << dd : 0u);       // unit starts inside [s0, s0 + 32)
+		const uint32_t before = __popc(__ballot_sync(FULL, pc < s0));                  // units that start before the window
+		const uint32_t i = before - 1u + __popc(heads & (0xFFFFFFFFu >> (31u - t)));
+		const uint4 d0 = stage[i], d1 = stage[32 + i];
+		const uint32_t pi = d0.x, wlo = d0.y, whi = d0.z, uA = d0.w, uB = d1.x, ush = d1.y;
 		const uint32_t k = s - pi, wcl = __popc(wlo), wcw = wcl + __popc(whi);
 		const bool isx = k >= wcw;                       // the unit's +x plane cell (only ever its last slot)
 		const uint32_t pos = isx ? XW : select64(wlo, whi, wcl, k, lut);
@@ -296,12 +315,11 @@ __device__ __forceinline__ void emit_group(const Ctx<RB> &cx, const uint64_t *lv
 		const uint32_t sh = ((sa >= lim) | (sb >= lim)) ? 64u : 0u;
 		uint32_t col;
 		if constexpr (L == 0) {
-			const uint32_t urlo = __shfl_sync(FULL, rlo, i), urhi = __shfl_sync(FULL, rhi, i);
-			const uint8_t *src = isx ? cx.nbx_xlo + (uB >> 16) : reinterpret_cast<const uint8_t *>(((unsigned long long)urhi << 32) | urlo) + pos;
+			const uint8_t *src = isx ? cx.nbx_xlo + (uB >> 16) : reinterpret_cast<const uint8_t *>(((unsigned long long)d1.w << 32) | d1.z) + pos;
 			col = __ldg(src);
 		} else {
-			const int uq = (gl * 32 + i) / NWl;
-			col = cx.template colour<L>(uq, (int)pos + 64 * ((gl * 32 + i) % NWl));
+			const int uu = (int)d1.z;                    // unit index inside the level
+			col = cx.template colour<L>(uu / NWl, (int)pos + 64 * (uu % NWl));
 		}
 		if (s0 + lane < S) {
 			const uint32_t rl = ((uA + xs) & 0xFFFFu) | (uA & 0xFFFF0000u);
@@ -317,7 +335,8 @@ struct SplatScratch {
 	uint64_t *pyr;                  // [slabs][LV_STRIDE]  level bit arrays of every non-empty slab
 	uint32_t *gp;                   // [slabs][GP_STRIDE]  exclusive prefix of the per-group splat counts
 	uint32_t *rec;                  // [slabs][kSlabRec]   per-level counts (count kernel) and bases (scan kernel)
-	unsigned long long *choff;      // [chunks]            byte offset of the chunk buffer in the arena (~0 = none)
+	unsigned long long *chrec;      // [chunks][kChunkRec] [0] byte offset of the chunk buffer in the arena (~0 = none),
+	                                //                     [1..4] own / +x face plane / +y / +z voxel pointers (0 = null chunk)
 };
 
 template <int RB>
@@ -331,7 +350,7 @@ __host__ __device__ __forceinline__ SplatScratch carve_scratch(uint8_t *base, si
 	sc.pyr = reinterpret_cast<uint64_t *>(base);
 	sc.gp = reinterpret_cast<uint32_t *>(base + slabs * G::LV_STRIDE * 8);
 	sc.rec = sc.gp + slabs * G::GP_STRIDE;
-	sc.choff = reinterpret_cast<unsigned long long *>(sc.rec + slabs * kSlabRec);
+	sc.chrec = reinterpret_cast<unsigned long long *>(sc.rec + slabs * kSlabRec);
 	return sc;
 }
 
@@ -405,7 +424,7 @@ __device__ __forceinline__ void chunk_reserve(const SplatScratch &sc, uint32_t c
 		if (off + bytes > st->capacity) { atomicExch(&st->overflow, 1u); off = ~0ull; }
 	}
 	if (lane == 0) {
-		sc.choff[chunk_i] = total ? off : ~0ull;
+		sc.chrec[(size_t)chunk_i * kChunkRec] = total ? off : ~0ull;
 		res->svl_offset = off;
 		res->svl_items_total = total * 4u;
 	}
@@ -448,6 +467,10 @@ k_splat_count(const VpWorldDev w, const uint32_t *__restrict__ ids, uint32_t n, 
 	uint32_t *rec = sc.rec + (size_t)blockIdx.x * kSlabRec;
 
 	VpResultDev *res = results + (result_pos ? result_pos[chunk_i] : chunk_i);
+	if (crank == 0 && tid < 4) {                      // the emit kernel takes the chunk's source pointers from here
+		const uint8_t *ptr = tid == 0 ? own : (tid == 1 ? nbx_xlo : (tid == 2 ? nby : nbz));
+		sc.chrec[(size_t)chunk_i * kChunkRec + 1 + tid] = (unsigned long long)ptr;
+	}
 	if (!own && !nbx_xlo && !nby && !nbz) {           // mesher.c:404-409: nothing can be visible
 		if (tid < 5) rec[tid] = 0;
 		chunk_reserve<CL>(sc, chunk_i, res, st);
@@ -742,6 +765,7 @@ k_splat_emit(const VpWorldDev w, const uint32_t *__restrict__ ids, uint32_t n, c
 	EmitMisc *misc = reinterpret_cast<EmitMisc *>(smem + G::E_OFF_MISC);
 
 	const int tid = threadIdx.x, lane = tid & 31;
+	uint4 *stage = reinterpret_cast<uint4 *>(smem + G::E_OFF_STAGE) + (tid >> 5) * 64;
 	const uint32_t slab = gridDim.x - 1 - blockIdx.x;        // last written first: the tail of the scratch is still in L2
 	const uint32_t chunk_i = slab / CL;
 	const int crank = CL > 1 ? (int)(slab % CL) : 0;
@@ -749,7 +773,8 @@ k_splat_emit(const VpWorldDev w, const uint32_t *__restrict__ ids, uint32_t n, c
 	const uint32_t *rec = sc.rec + (size_t)slab * kSlabRec;
 	const uint32_t c0 = rec[0], c1 = rec[1], c2 = rec[2], c3 = rec[3], c4 = rec[4];
 	if ((c0 | c1 | c2 | c3 | c4) == 0) return;
-	const unsigned long long choff = sc.choff[chunk_i];
+	const unsigned long long *chrec = sc.chrec + (size_t)chunk_i * kChunkRec;
+	const unsigned long long choff = chrec[0];
 	if (choff == ~0ull) return;                               // arena overflow: nothing was reserved
 	if (tid == 0) {
 		mbar_init(&misc->bar, 1);
@@ -760,10 +785,12 @@ k_splat_emit(const VpWorldDev w, const uint32_t *__restrict__ ids, uint32_t n, c
 		tma_load_1d(lut, kSelLut.v, 2048, &misc->bar);
 		tma_load_1d(gpre, sc.gp + (size_t)slab * G::GP_STRIDE, G::GP_STRIDE * 4, &misc->bar);
 	}
-	const ChunkRefs<RB> ch(w, ids[chunk_i]);
+	const uint32_t cid = ids[chunk_i];
+	const uint32_t ccx = cid & ((1u << w.bits[0]) - 1), ccy = (cid >> w.bits[0]) & ((1u << w.bits[1]) - 1), ccz = cid >> (w.bits[0] + w.bits[1]);
 	const int z0 = crank * ZS;
 	const uint32_t b0 = rec[8], b1 = rec[9], b2 = rec[10], b3 = rec[11], b4 = rec[12];
-	Ctx<RB> cx_{w, lv, ch.own, ch.nbx_xlo, ch.nby, ch.nbz, z0, (uint32_t)ch.cx << RB, (uint32_t)ch.cy << RB, (uint32_t)ch.cz << RB};
+	Ctx<RB> cx_{w, lv, reinterpret_cast<const uint8_t *>(chrec[1]), reinterpret_cast<const uint8_t *>(chrec[2]),
+	            reinterpret_cast<const uint8_t *>(chrec[3]), reinterpret_cast<const uint8_t *>(chrec[4]), z0, ccx << RB, ccy << RB, ccz << RB};
 	uint2 *out2 = reinterpret_cast<uint2 *>(arena + choff);
 	__syncthreads();
 	mbar_wait(&misc->bar, 0);
@@ -773,18 +800,22 @@ k_splat_emit(const VpWorldDev w, const uint32_t *__restrict__ ids, uint32_t n, c
 	// per round whatever the distribution of visible voxels, and the 8-byte stores of a warp are contiguous.
 	const uint32_t nne = gpre[G::NG + 1];
 	const uint8_t *glist = reinterpret_cast<const uint8_t *>(gpre + G::NG + 2);
+#if VP_EMIT_STATIC
+	for (uint32_t k = (uint32_t)(tid >> 5); k < nne; k += kEmitWarps) {
+#else
 	for (;;) {
 		uint32_t k = 0;
 		if (lane == 0) k = atomicAdd(&misc->next, 1u);
 		k = __shfl_sync(0xffffffffu, k, 0);
 		if (k >= nne) break;
+#endif
 		const int g = glist[k];
 		const uint32_t gs = gpre[g];
-		if (g < G::grp_off(1)) emit_group<RB, 0>(cx_, lv, lut, g, out2 + b0 + (gs - gpre[0]), lane);
-		else if (g < G::grp_off(2)) emit_group<RB, 1>(cx_, lv, lut, g - G::grp_off(1), out2 + b1 + (gs - gpre[G::grp_off(1)]), lane);
-		else if (g < G::grp_off(3)) emit_group<RB, 2>(cx_, lv, lut, g - G::grp_off(2), out2 + b2 + (gs - gpre[G::grp_off(2)]), lane);
-		else if (g < G::grp_off(4)) emit_group<RB, 3>(cx_, lv, lut, g - G::grp_off(3), out2 + b3 + (gs - gpre[G::grp_off(3)]), lane);
-		else emit_group<RB, 4>(cx_, lv, lut, g - G::grp_off(4), out2 + b4 + (gs - gpre[G::grp_off(4)]), lane);
+		if (g < G::grp_off(1)) emit_group<RB, 0>(cx_, lv, lut, stage, g, out2 + b0 + (gs - gpre[0]), lane);
+		else if (g < G::grp_off(2)) emit_group<RB, 1>(cx_, lv, lut, stage, g - G::grp_off(1), out2 + b1 + (gs - gpre[G::grp_off(1)]), lane);
+		else if (g < G::grp_off(3)) emit_group<RB, 2>(cx_, lv, lut, stage, g - G::grp_off(2), out2 + b2 + (gs - gpre[G::grp_off(2)]), lane);
+		else if (g < G::grp_off(4)) emit_group<RB, 3>(cx_, lv, lut, stage, g - G::grp_off(3), out2 + b3 + (gs - gpre[G::grp_off(3)]), lane);
+		else emit_group<RB, 4>(cx_, lv, lut, stage, g - G::grp_off(4), out2 + b4 + (gs - gpre[G::grp_off(4)]), lane);
 	}
 }
 
@@ -814,7 +845,7 @@ template <int RB> size_t scratch_bytes(uint32_t n)
 {
 	using G = Geo<RB>;
 	const size_t slabs = (size_t)n * G::CL;
-	return arrived_region_bytes(n) + slabs * ((size_t)G::LV_STRIDE * 8 + (size_t)G::GP_STRIDE * 4 + kSlabRec * 4) + (size_t)n * 8 + 256;
+	return arrived_region_bytes(n) + slabs * ((size_t)G::LV_STRIDE * 8 + (size_t)G::GP_STRIDE * 4 + kSlabRec * 4) + (size_t)n * kChunkRec * 8 + 256;
 }
 
 } // namespace
