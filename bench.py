@@ -45,8 +45,11 @@ def world_bits(n_gpus):
 
 def workload_name(bits):
     R = 1 << ROOT_BITW
-    return "%dx%dx%d voxels, chunk %d^3, full rebuild: splat(5 LOD) all chunks + mesh within 512 of camera" % (
+    name = "%dx%dx%d voxels, chunk %d^3, full rebuild: splat(5 LOD) all chunks + mesh within 512 of camera" % (
         (1 << bits[0]) * R, (1 << bits[1]) * R, (1 << bits[2]) * R, R)
+    if WORKLOAD == "c2" and tuple(bits) != tuple(BASE_BITS):
+        name += " (the 2048x256x2048 world repeated %d times along z: identical work per GPU)" % (1 << (bits[2] - BASE_BITS[2]))
+    return name
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -114,7 +117,15 @@ def generate_slab(bits, z0, z1):
     N = R ** 3
     zg1 = min(z1 + 1, nz)                                   # one extra row: the shadow reach crosses the border
     ids = np.arange(z0 * per_row, zg1 * per_row, dtype=np.uint32)
-    dense, solid = worldgen.gen_chunks(SEED, ROOT_BITW, bits, ids)
+    if WORKLOAD == "c2" and bits != BASE_BITS:
+        # weak scaling: the world is the base world (one GPU's 2048x256x2048) repeated along z, so every rank rebuilds
+        # exactly the same content -- a larger generated world has other terrain statistics (the generator's edge
+        # fall-off is relative to the world size) and the per-GPU work would drift with N
+        base_rows = 1 << BASE_BITS[2]
+        base_ids = ((ids // per_row) % base_rows) * per_row + ids % per_row
+        dense, solid = worldgen.gen_chunks(SEED, ROOT_BITW, BASE_BITS, base_ids.astype(np.uint32))
+    else:
+        dense, solid = worldgen.gen_chunks(SEED, ROOT_BITW, bits, ids)
     ptrs = [0] * (per_row * nz)
     base = dense.ctypes.data
     for k, cid in enumerate(ids):
@@ -274,8 +285,7 @@ def run_native(args):
         ctx.batch_prepare(own_ids, per_chunk_flags=flags)
 
         def step():
-            rebuilder.exchange_halos(mesh=True)
-            ctx.rebuild_device()
+            rebuilder.rebuild_step(mesh=True)        # border exchange overlapped with the chunks that do not read a ghost row
 
         def barrier():
             torch.cuda.synchronize()

@@ -166,6 +166,10 @@ VP_API int  vp_rebuild_from_rle(vp_ctx *ctx, const uint32_t *chunk_ids, uint32_t
 VP_API int  vp_batch_prepare(vp_ctx *ctx, const uint32_t *chunk_ids, uint32_t n, const uint8_t *per_chunk_flags,
                       uint32_t flags);
 VP_API int  vp_rebuild_device(vp_ctx *ctx);
+/* The same in two parts, for slab contexts that exchange border planes every step: part 0 launches the chunks that do
+ * not read a ghost row (all but the slab's last chunk row for splats, plus the first row for meshes), part 1 the
+ * others -- call it after vp_halo_unpack, so the exchange overlaps part 0.  vp_rebuild_device == part 0 + part 1. */
+VP_API int  vp_rebuild_device_part(vp_ctx *ctx, int part);
 VP_API int  vp_rebuild_device_results(vp_ctx *ctx, vp_chunk_result *results, uint64_t *splat_bytes, uint64_t *mesh_bytes);
 /* Device time of the kernels of the last n (<= 256) vp_rebuild_device calls, oldest first (CUDA events on the
  * context stream): splat_ms[k] = cull+LOD+splat kernel, mesh_ms[k] = mesh kernel (0 if not launched).

@@ -41,6 +41,24 @@ def main():
             rbld = slab.SlabRebuilder(ctx, rank, ws, lambda n: torch.empty(n, dtype=torch.uint8, device="cuda"), dist=dist)
             rbld.exchange_halos(mesh=True)
             res, splat, mesh = ctx.rebuild_batch(own, vpb.VP_REBUILD_SPLAT | vpb.VP_REBUILD_MESH)
+            # the device-resident step with the exchange hidden behind the chunks that do not read a ghost row must
+            # give the same buffers (arena offsets may differ: compare per chunk)
+            ctx.batch_prepare(own, vpb.VP_REBUILD_SPLAT | vpb.VP_REBUILD_MESH)
+            rbld.rebuild_step(mesh=True)
+            res2, sb2, mb2 = ctx.rebuild_device_results()
+            splat2, mesh2 = ctx.arena_download(0, sb2), ctx.arena_download(1, mb2)
+        for k in range(len(own)):
+            same = np.array_equal(res2["svl_items"][k], res["svl_items"][k]) and res2["vbo_items"][k] == res["vbo_items"][k] and res2["ibo_items"][k] == res["ibo_items"][k]
+            if same:
+                a, b, nb = int(res["svl_offset"][k]), int(res2["svl_offset"][k]), int(res["svl_items_total"][k]) * 2
+                same = np.array_equal(splat[a:a + nb], splat2[b:b + nb])
+                a, b, nb = int(res["vbo_offset"][k]), int(res2["vbo_offset"][k]), int(res["vbo_items"][k]) * 2
+                same = same and np.array_equal(mesh[a:a + nb], mesh2[b:b + nb])
+                a, b, nb = int(res["ibo_offset"][k]), int(res2["ibo_offset"][k]), int(res["ibo_items"][k]) * 4
+                same = same and np.array_equal(mesh[a:a + nb], mesh2[b:b + nb])
+            if not same:
+                failures += 1
+                print("rank %d: chunk %d of world rb=%d %s: overlapped step differs from rebuild_batch" % (rank, own[k], rb, bits), flush=True)
         for k, cid in enumerate(own):
             g, it = o.splat(int(cid))
             off = int(res["svl_offset"][k])

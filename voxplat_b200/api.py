@@ -83,6 +83,7 @@ def load_library():
         "vp_rebuild_from_rle": (C.c_int, [vp, vp, C.c_uint32, vp, vp, C.c_uint32, vp, C.c_uint32, vp, C.POINTER(vp), C.POINTER(vp)]),
         "vp_batch_prepare": (C.c_int, [vp, vp, C.c_uint32, vp, C.c_uint32]),
         "vp_rebuild_device": (C.c_int, [vp]),
+        "vp_rebuild_device_part": (C.c_int, [vp, C.c_int]),
         "vp_rebuild_device_results": (C.c_int, [vp, vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
         "vp_kernel_ms_history": (C.c_int, [vp, C.c_uint32, vp, vp]),
         "vp_splat_arena_device": (vp, [vp]),
@@ -280,6 +281,10 @@ class Context:
 
     def rebuild_device(self):
         self._ck(self.lib.vp_rebuild_device(self.h))
+
+    def rebuild_device_part(self, part):
+        """part 0: chunks that do not read a ghost row; part 1 (after halo_unpack): the slab's border chunks."""
+        self._ck(self.lib.vp_rebuild_device_part(self.h, part))
 
     def rebuild_device_results(self):
         res = np.zeros(self._batch_n, RESULT_DTYPE)

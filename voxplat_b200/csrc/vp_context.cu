@@ -497,6 +497,30 @@ extern "C" int vp_batch_prepare(vp_ctx *c, const uint32_t *ids, uint32_t n, cons
 		}
 		if (f & VP_REBUILD_MESH) { mid.push_back(ids[i]); mpos.push_back(i); }
 	}
+	// Chunks whose rebuild reads a ghost row (the border plane a slab neighbour sends every step) go to the END of the
+	// lists: vp_rebuild_device_part(0) launches the others while the exchange is still in flight, part 1 the rest.
+	// splat: only the +z neighbour row matters (mesher.c:391-432); mesh AO looks both ways (mesher.c:119-171).
+	{
+		const uint32_t per_row = (uint32_t)c->nx * c->ny;
+		auto needs_ghost = [&](uint32_t id, bool mesh) {
+			const int cz = (int)(id / per_row);
+			if (cz + 1 == c->cfg.slab_z1 && c->cfg.slab_z1 < c->nz) return true;
+			return mesh && cz == c->cfg.slab_z0 && c->cfg.slab_z0 > 0;
+		};
+		auto interior_first = [&](std::vector<uint32_t> &ids_, std::vector<uint32_t> &pos_, bool mesh) -> uint32_t {
+			std::vector<uint32_t> a, ap, b, bp;
+			for (size_t k = 0; k < ids_.size(); k++) {
+				if (needs_ghost(ids_[k], mesh)) { b.push_back(ids_[k]); bp.push_back(pos_[k]); }
+				else { a.push_back(ids_[k]); ap.push_back(pos_[k]); }
+			}
+			const uint32_t n_int = (uint32_t)a.size();
+			a.insert(a.end(), b.begin(), b.end()); ap.insert(ap.end(), bp.begin(), bp.end());
+			ids_.swap(a); pos_.swap(ap);
+			return n_int;
+		};
+		c->n_splat_int = interior_first(sid, spos, false);
+		c->n_mesh_int = interior_first(mid, mpos, true);
+	}
 	c->batch_n = n; c->n_splat = (uint32_t)sid.size(); c->n_mesh = (uint32_t)mid.size();
 	if ((rc = splat_scratch_reserve(c, c->n_splat))) return rc;
 	if (c->n_splat) {
@@ -516,44 +540,59 @@ extern "C" int vp_batch_prepare(vp_ctx *c, const uint32_t *ids, uint32_t n, cons
 	return VP_OK;
 }
 
-extern "C" int vp_rebuild_device(vp_ctx *c)
+// part 0: reset the arenas / records, launch the chunks that do not read a ghost row; part 1: the chunks that do (after
+// the caller unpacked the received border planes on the context stream).  Within a part the mesh kernel (few chunks,
+// latency bound) runs on its own stream beside the splat kernels: the two write disjoint fields of the result records
+// and separate arenas.
+extern "C" int vp_rebuild_device_part(vp_ctx *c, int part)
 {
-	if (!c) return VP_ERR_ARG;
+	if (!c || part < 0 || part > 1) return VP_ERR_ARG;
 	VP_CUDA(c, cudaSetDevice(c->cfg.device));
-	VP_CUDA(c, cudaMemcpyAsync(c->d_arena_state, c->h_arena_state + 3, 2 * sizeof(VpArenaDev), cudaMemcpyHostToDevice, c->stream));
-	VP_CUDA(c, cudaMemsetAsync(c->d_results, 0, (size_t)c->batch_n * sizeof(VpResultDev), c->stream));
 	VpWorldDev w = vp_world_dev(c);
-	cudaEvent_t *ev = c->ev_k[c->rebuilds % vp_ctx::kHist];
-	uint8_t &valid = c->ev_k_valid[c->rebuilds % vp_ctx::kHist];
-	valid = 0;
-	c->rebuilds++;
-	// The mesh kernel (few chunks, latency bound) runs on its own stream beside the splat kernels: the two write
-	// disjoint fields of the result records and separate arenas.
+	if (part == 0) {
+		VP_CUDA(c, cudaMemcpyAsync(c->d_arena_state, c->h_arena_state + 3, 2 * sizeof(VpArenaDev), cudaMemcpyHostToDevice, c->stream));
+		VP_CUDA(c, cudaMemsetAsync(c->d_results, 0, (size_t)c->batch_n * sizeof(VpResultDev), c->stream));
+		c->ev_k_valid[c->rebuilds % vp_ctx::kHist] = 0;
+		c->rebuilds++;
+	}
+	if (!c->rebuilds) return vp_fail(c, VP_ERR_ARG, "vp_rebuild_device_part: part 1 before part 0");
+	cudaEvent_t *ev = c->ev_k[(c->rebuilds - 1) % vp_ctx::kHist];
+	uint8_t &valid = c->ev_k_valid[(c->rebuilds - 1) % vp_ctx::kHist];
+	const uint32_t s0 = part ? c->n_splat_int : 0, s1 = part ? c->n_splat : c->n_splat_int;
+	const uint32_t m0 = part ? c->n_mesh_int : 0, m1 = part ? c->n_mesh : c->n_mesh_int;
 	const bool fork = c->n_splat && c->n_mesh;
 	cudaStream_t ms = fork ? c->mesh_stream : c->stream;
-	if (fork) {
+	if (fork && (part == 0 || m1 > m0)) {
 		VP_CUDA(c, cudaEventRecord(c->ev_fork, c->stream));
 		VP_CUDA(c, cudaStreamWaitEvent(ms, c->ev_fork, 0));
 	}
 	if (c->n_mesh) {
-		VP_CUDA(c, cudaEventRecord(ev[2], ms));
-		VP_CUDA(c, vp_launch_mesh(w, c->d_mesh_ids, c->n_mesh, c->d_results, c->d_mesh_pos, c->d_mesh_arena, c->d_arena_state + 1, ms));
-		VP_CUDA(c, cudaEventRecord(ev[3], ms));
-		valid |= 2;
-		c->launches++;
+		if (part == 0) VP_CUDA(c, cudaEventRecord(ev[2], ms));
+		if (m1 > m0) {
+			VP_CUDA(c, vp_launch_mesh(w, c->d_mesh_ids + m0, m1 - m0, c->d_results, c->d_mesh_pos + m0, c->d_mesh_arena, c->d_arena_state + 1, ms));
+			c->launches++;
+		}
+		if (part == 1) { VP_CUDA(c, cudaEventRecord(ev[3], ms)); valid |= 2; }
 	}
 	if (c->n_splat) {
-		VP_CUDA(c, cudaEventRecord(ev[0], c->stream));
-		VP_CUDA(c, vp_launch_splat(w, c->d_splat_ids, c->n_splat, c->d_results, c->d_splat_pos, c->d_splat_arena, c->d_arena_state + 0, c->d_splat_scratch, c->splat_scratch_chunks, c->stream));
-		VP_CUDA(c, cudaEventRecord(ev[1], c->stream));
-		valid |= 1;
-		c->launches += kSplatLaunches;
+		if (part == 0) VP_CUDA(c, cudaEventRecord(ev[0], c->stream));
+		if (s1 > s0) {
+			VP_CUDA(c, vp_launch_splat(w, c->d_splat_ids + s0, s1 - s0, c->d_results, c->d_splat_pos + s0, c->d_splat_arena, c->d_arena_state + 0, c->d_splat_scratch, c->splat_scratch_chunks, c->stream));
+			c->launches += kSplatLaunches;
+		}
+		if (part == 1) { VP_CUDA(c, cudaEventRecord(ev[1], c->stream)); valid |= 1; }
 	}
-	if (fork) {
+	if (fork && part == 1) {
 		VP_CUDA(c, cudaEventRecord(c->ev_join, ms));
 		VP_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_join, 0));
 	}
 	return VP_OK;
+}
+
+extern "C" int vp_rebuild_device(vp_ctx *c)
+{
+	int rc = vp_rebuild_device_part(c, 0);
+	return rc ? rc : vp_rebuild_device_part(c, 1);
 }
 
 extern "C" int vp_rebuild_device_results(vp_ctx *c, vp_chunk_result *results, uint64_t *splat_bytes, uint64_t *mesh_bytes)

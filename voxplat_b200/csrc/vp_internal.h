@@ -83,6 +83,7 @@ struct vp_ctx {
 	// batch state
 	uint32_t *d_ids; uint8_t *d_flags; uint32_t batch_n, batch_cap; uint32_t batch_flags;
 	uint32_t *d_splat_ids, *d_mesh_ids; uint32_t n_splat, n_mesh;
+	uint32_t n_splat_int, n_mesh_int;                    // list entries that do not read a ghost row come first
 	uint32_t *d_splat_pos, *d_mesh_pos;                  // position in the batch of each list entry
 	int32_t *d_tmp_slots;                                // scratch list of slots for helper kernels
 	VpResultDev *d_results; VpResultDev *h_results;      // h_results pinned

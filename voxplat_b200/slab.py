@@ -48,10 +48,12 @@ class SlabRebuilder:
         self.buf = {("send", 0): make_buffer(n), ("recv", 0): make_buffer(n),
                     ("send", 1): make_buffer(n), ("recv", 1): make_buffer(n)}
 
-    def exchange_halos(self, mesh=False):
-        """Pack my border planes, swap them with the slab neighbours, unpack into the ghost rows."""
+    def exchange_begin(self, mesh=False):
+        """Pack my border planes and start the swap with the slab neighbours; returns the pending requests.
+        NCCL runs the transfer on its own stream, so kernels queued next on the context stream (the rebuild of the
+        chunks that do not read a ghost row) overlap it."""
         if self.world_size == 1:
-            return 0
+            return None
         plan = halo_schedule(self.rank, self.world_size, mesh)
         for op, which, _ in plan:
             if op == "send":
@@ -60,13 +62,32 @@ class SlabRebuilder:
         for op, which, peer in plan:
             fn = self.dist.isend if op == "send" else self.dist.irecv
             ops.append(self.dist.P2POp(fn, self.buf[(op, which)], peer, group=self.group))
-        if ops:
-            for req in self.dist.batch_isend_irecv(ops):
-                req.wait()
+        reqs = self.dist.batch_isend_irecv(ops) if ops else []
+        return plan, reqs
+
+    def exchange_finish(self, pending):
+        """Wait for the swap started by exchange_begin and unpack the received planes into the ghost rows."""
+        if pending is None:
+            return 0
+        plan, reqs = pending
+        for req in reqs:
+            req.wait()
         for op, which, _ in plan:
             if op == "recv":
                 self.store.halo_unpack(which, self.buf[(op, which)].data_ptr())
         return len(plan)
+
+    def exchange_halos(self, mesh=False):
+        """Pack my border planes, swap them with the slab neighbours, unpack into the ghost rows."""
+        return self.exchange_finish(self.exchange_begin(mesh))
+
+    def rebuild_step(self, mesh=True):
+        """One device-resident rebuild of the prepared batch with the border exchange hidden behind the chunks that do
+        not need it (store = a voxplat_b200.Context)."""
+        pending = self.exchange_begin(mesh)
+        self.store.rebuild_device_part(0)
+        self.exchange_finish(pending)
+        self.store.rebuild_device_part(1)
 
 
 def near_camera_flags(ids, root_bitw, max_bitw, camera=(64.0, 128.0, 64.0), radius=512.0):
