@@ -2,6 +2,7 @@
 // uploads, batch rebuild orchestration, staging.  No CPU compute path exists here: every data
 // transformation is a CUDA kernel (vp_splat.cu, vp_mesh.cu, vp_rle.cu, the small kernels below).
 #include "vp_internal.h"
+#include <atomic>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -144,12 +145,20 @@ extern "C" int vp_ctx_create(const vp_config *cfg, vp_ctx **out)
 	CK(cudaSetDevice(cfg->device));
 	CK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
 	CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-	CK(cudaStreamCreateWithFlags(&c->mesh_stream, cudaStreamNonBlocking));
+	{
+		// VP_MESH_PRIO=hi|lo: scheduling priority of the mesh kernel relative to the splat kernels it runs beside
+		int lo = 0, hi = 0;
+		CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+		const char *e = getenv("VP_MESH_PRIO");
+		const int prio = (e && e[0] == 'h') ? hi : ((e && e[0] == 'l') ? lo : 0);
+		CK(cudaStreamCreateWithPriority(&c->mesh_stream, cudaStreamNonBlocking, prio));
+	}
 	CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
 	CK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
 	CK(cudaStreamCreateWithFlags(&c->down_stream, cudaStreamNonBlocking));
 	for (int k = 0; k < 2; k++) for (int i = 0; i < 64; i++) CK(cudaEventCreateWithFlags(&c->ev_pipe[k][i], cudaEventDisableTiming));
-	CK(cudaHostAlloc(&c->h_steps, 64 * 2 * sizeof(VpArenaDev), cudaHostAllocDefault));
+	CK(cudaHostAlloc(&c->h_steps, 64 * 2 * sizeof(VpArenaDev) + 64 * sizeof(uint32_t), cudaHostAllocDefault));
+	memset(c->h_steps, 0, 64 * 2 * sizeof(VpArenaDev) + 64 * sizeof(uint32_t));
 	CK(cudaEventCreateWithFlags(&c->ev_a, cudaEventDisableTiming));
 	CK(cudaEventCreateWithFlags(&c->ev_b, cudaEventDisableTiming));
 	for (int h = 0; h < vp_ctx::kHist; h++) for (int i = 0; i < 4; i++) CK(cudaEventCreate(&c->ev_k[h][i]));
@@ -435,6 +444,17 @@ extern "C" int vp_upload_shadow_rows(vp_ctx *c, uint32_t z0, uint32_t z1, const 
 // ------------------------------------------------------------------------------------------------
 // rebuild
 // ------------------------------------------------------------------------------------------------
+
+// Pipeline step done: the arena states go straight into pinned host memory (zero-copy stores) followed by the step's
+// ticket.  A cudaMemcpyAsync would queue behind the multi-megabyte downloads on the device-to-host copy engine and make
+// every step look as long as a download; the host polls the ticket instead of sleeping on an event.
+__global__ void k_publish_step(const VpArenaDev *__restrict__ d_state, VpArenaDev *h_state, volatile uint32_t *h_ticket, uint32_t ticket)
+{
+	if (threadIdx.x < 2) h_state[threadIdx.x] = d_state[threadIdx.x];
+	__threadfence_system();
+	__syncwarp();
+	if (threadIdx.x == 0) *h_ticket = ticket;
+}
 
 static int batch_reserve(vp_ctx *c, uint32_t n)
 {
@@ -931,6 +951,7 @@ extern "C" int vp_rebuild_from_rle(vp_ctx *c, const uint32_t *ids, uint32_t n, c
                                    uint32_t flags, const uint8_t *per_chunk_flags, uint32_t n_blocks,
                                    vp_chunk_result *results, const void **splat_base, const void **mesh_base)
 {
+	const double t_entry = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
 	if (!c || !n || !ids || !words || !word_offsets || !results) return vp_fail(c, VP_ERR_ARG, "vp_rebuild_from_rle: null argument");
 	VP_CUDA(c, cudaSetDevice(c->cfg.device));
 	bool ascending = true;
@@ -1027,6 +1048,43 @@ extern "C" int vp_rebuild_from_rle(vp_ctx *c, const uint32_t *ids, uint32_t n, c
 	VP_CUDA(c, cudaEventRecord(c->ev_a, c->stream));
 	VP_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev_a, 0));
 
+	// ---- download every step's new output range as soon as its kernels are done ----
+	// Steps publish their arena cursors + a ticket in pinned memory (k_publish_step); drain() turns every finished step
+	// into two asynchronous downloads on down_stream, either opportunistically (while later steps are still being
+	// enqueued) or to the end (polling the tickets: the wake-up latency of an event wait would leave the copy engine idle
+	// between steps).
+	const bool trace = getenv("VP_TRACE") != nullptr;
+	auto now_ms = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+	volatile uint32_t *tickets = reinterpret_cast<volatile uint32_t *>(c->h_steps + 64 * 2);
+	const uint32_t ticket = ++c->pipe_ticket ? c->pipe_ticket : ++c->pipe_ticket;          // never 0
+	uint64_t done_s = 0, done_m = 0;
+	uint32_t next_dl = 0, enqueued_steps = 0;
+	bool staged = true;
+	auto drain = [&](bool to_the_end) -> int {
+		while (next_dl < (to_the_end ? n_blocks : enqueued_steps)) {
+			const uint32_t t = next_dl;
+			if (tickets[t] != ticket) {
+				if (!to_the_end) return VP_OK;
+				const cudaError_t q = cudaEventQuery(c->ev_pipe[1][t]);                          // surfaces launch failures instead of spinning forever
+				if (q != cudaSuccess && q != cudaErrorNotReady) return vp_fail(c, VP_ERR_CUDA, "vp_rebuild_from_rle: pipeline step", q);
+				if (q == cudaSuccess && tickets[t] != ticket) { std::atomic_thread_fence(std::memory_order_seq_cst); }
+				continue;
+			}
+			std::atomic_thread_fence(std::memory_order_acquire);
+			next_dl++;
+			if (trace) fprintf(stderr, "[vp_rebuild_from_rle] step %u kernels done at %.3f ms\n", t, now_ms() - t_entry);
+			const uint64_t cs = c->h_steps[2 * t].cursor, cm = c->h_steps[2 * t + 1].cursor;
+			if (c->h_steps[2 * t].overflow || c->h_steps[2 * t + 1].overflow) { staged = false; next_dl = n_blocks; return VP_OK; }
+			if (cs > c->splat_stage_cap || cm > c->mesh_stage_cap) { staged = false; continue; }      // staging too small: bulk copy below
+			if (!staged) continue;
+			VP_CUDA(c, cudaStreamWaitEvent(c->down_stream, c->ev_pipe[1][t], 0));
+			if (cs > done_s) VP_CUDA(c, cudaMemcpyAsync(c->h_splat_stage + done_s, c->d_splat_arena + done_s, cs - done_s, cudaMemcpyDeviceToHost, c->down_stream));
+			if (cm > done_m) VP_CUDA(c, cudaMemcpyAsync(c->h_mesh_stage + done_m, c->d_mesh_arena + done_m, cm - done_m, cudaMemcpyDeviceToHost, c->down_stream));
+			done_s = cs; done_m = cm;
+		}
+		return VP_OK;
+	};
+
 	// ---- enqueue: upload+decode on copy_stream, kernels on the main stream ----
 	VpWorldDev w = vp_world_dev(c);
 	for (uint32_t t = 0; t < n_blocks; t++) {
@@ -1038,6 +1096,7 @@ extern "C" int vp_rebuild_from_rle(vp_ctx *c, const uint32_t *ids, uint32_t n, c
 		VP_CUDA(c, cudaEventRecord(c->ev_pipe[0][t], c->copy_stream));
 		c->launches += 2;
 		VP_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_pipe[0][t], 0));
+		enqueued_steps = t + 1;
 		if (s_first[t + 1] > s_first[t]) {
 			VP_CUDA(c, vp_launch_splat(w, c->d_splat_ids + s_first[t], s_first[t + 1] - s_first[t], c->d_results, c->d_splat_pos + s_first[t], c->d_splat_arena, c->d_arena_state + 0, c->d_splat_scratch, c->splat_scratch_chunks, c->stream));
 			c->launches += kSplatLaunches;
@@ -1046,27 +1105,18 @@ extern "C" int vp_rebuild_from_rle(vp_ctx *c, const uint32_t *ids, uint32_t n, c
 			VP_CUDA(c, vp_launch_mesh(w, c->d_mesh_ids + m_first[t], m_first[t + 1] - m_first[t], c->d_results, c->d_mesh_pos + m_first[t], c->d_mesh_arena, c->d_arena_state + 1, c->stream));
 			c->launches++;
 		}
-		VP_CUDA(c, cudaMemcpyAsync(c->h_steps + 2 * t, c->d_arena_state, 2 * sizeof(VpArenaDev), cudaMemcpyDeviceToHost, c->stream));
+		k_publish_step<<<1, 32, 0, c->stream>>>(c->d_arena_state, c->h_steps + 2 * t, tickets + t, ticket);
+		VP_CUDA(c, cudaGetLastError());
+		c->launches++;
 		VP_CUDA(c, cudaEventRecord(c->ev_pipe[1][t], c->stream));
+		if ((rc = drain(false))) return rc;           // start the downloads of finished steps while the later ones are enqueued
 	}
 	VP_CUDA(c, cudaMemcpyAsync(c->h_results, c->d_results, (size_t)n * sizeof(VpResultDev), cudaMemcpyDeviceToHost, c->stream));
-
-	// ---- download every step's new output range as soon as its kernels are done ----
-	uint64_t done_s = 0, done_m = 0;
-	bool staged = true;
-	for (uint32_t t = 0; t < n_blocks; t++) {
-		VP_CUDA(c, cudaEventSynchronize(c->ev_pipe[1][t]));
-		const uint64_t cs = c->h_steps[2 * t].cursor, cm = c->h_steps[2 * t + 1].cursor;
-		if (c->h_steps[2 * t].overflow || c->h_steps[2 * t + 1].overflow) { staged = false; break; }
-		if (cs > c->splat_stage_cap || cm > c->mesh_stage_cap) { staged = false; continue; }       // staging too small: bulk copy below
-		if (!staged) continue;
-		VP_CUDA(c, cudaStreamWaitEvent(c->down_stream, c->ev_pipe[1][t], 0));
-		if (cs > done_s) VP_CUDA(c, cudaMemcpyAsync(c->h_splat_stage + done_s, c->d_splat_arena + done_s, cs - done_s, cudaMemcpyDeviceToHost, c->down_stream));
-		if (cm > done_m) VP_CUDA(c, cudaMemcpyAsync(c->h_mesh_stage + done_m, c->d_mesh_arena + done_m, cm - done_m, cudaMemcpyDeviceToHost, c->down_stream));
-		done_s = cs; done_m = cm;
-	}
+	if (trace) fprintf(stderr, "[vp_rebuild_from_rle] enqueued after %.3f ms\n", now_ms() - t_entry);
+	if ((rc = drain(true))) return rc;
 	VP_CUDA(c, cudaStreamSynchronize(c->stream));
 	VP_CUDA(c, cudaStreamSynchronize(c->down_stream));
+	if (trace) fprintf(stderr, "[vp_rebuild_from_rle] downloads done at %.3f ms\n", now_ms() - t_entry);
 	uint32_t status = 0;
 	VP_CUDA(c, cudaMemcpy(&status, d_status, 4, cudaMemcpyDeviceToHost));
 	VP_CUDA(c, cudaMemcpy(c->h_arena_state, c->d_arena_state, 2 * sizeof(VpArenaDev), cudaMemcpyDeviceToHost));

@@ -66,7 +66,8 @@ struct vp_ctx {
 	cudaStream_t mesh_stream;     // the mesh kernel of a rebuild runs beside the splat kernels
 	cudaEvent_t ev_fork, ev_join;
 	cudaEvent_t ev_pipe[2][64];   // [0] decode done, [1] kernels done, per pipeline step
-	VpArenaDev *h_steps;          // pinned: arena states after every pipeline step [64][2]
+	VpArenaDev *h_steps;          // pinned: arena states after every pipeline step [64][2], then 64 uint32 step tickets
+	uint32_t pipe_ticket;         // ticket value of the running / last vp_rebuild_from_rle call
 	uint64_t last_splat_bytes, last_mesh_bytes;
 	cudaEvent_t ev_a, ev_b;
 	static constexpr int kHist = 256;
