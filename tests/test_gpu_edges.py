@@ -59,3 +59,37 @@ def test_bad_ids_are_rejected_and_duplicates_work():
             assert np.array_equal(splat[off:off + g.size * 2].view(np.int16), g)
     finally:
         ctx.close()
+
+
+def test_rebuild_in_two_parts_equals_one_call():
+    """vp_rebuild_device_part(0) + (1) (the slab step that hides the border exchange) on a single-slab context and on a
+    middle slab: same buffers per chunk as vp_rebuild_device."""
+    w = worldgen.World(11, 5, (1, 1, 3))
+    per_row = 4
+    for slab_rows in [None, (2, 5)]:
+        ctx = vpb.Context(5, (1, 1, 3), slab=slab_rows) if slab_rows else vpb.Context(5, (1, 1, 3))
+        try:
+            z0, z1 = slab_rows if slab_rows else (0, 8)
+            own = np.arange(z0 * per_row, z1 * per_row, dtype=np.uint32)
+            nn = own[w.solid[own] > 0]
+            ctx.upload_chunks_dense(nn, np.ascontiguousarray(w.dense[nn]))
+            ctx.upload_shadow_rows(0, w.shadow[:w.shw * w.dims[2]])
+            ctx.batch_prepare(own, flags=vpb.VP_REBUILD_SPLAT | vpb.VP_REBUILD_MESH)
+            ctx.rebuild_device()
+            r1, sb1, mb1 = ctx.rebuild_device_results()
+            s1, m1 = ctx.arena_download(0, sb1), ctx.arena_download(1, mb1)
+            ctx.rebuild_device_part(0)
+            ctx.rebuild_device_part(1)
+            r2, sb2, mb2 = ctx.rebuild_device_results()
+            s2, m2 = ctx.arena_download(0, sb2), ctx.arena_download(1, mb2)
+            assert sb1 == sb2 and mb1 == mb2
+            for k in range(len(own)):
+                assert np.array_equal(r1["svl_items"][k], r2["svl_items"][k]) and r1["vbo_items"][k] == r2["vbo_items"][k]
+                a, b, nb = int(r1["svl_offset"][k]), int(r2["svl_offset"][k]), int(r1["svl_items_total"][k]) * 2
+                assert np.array_equal(s1[a:a + nb], s2[b:b + nb])
+                a, b, nb = int(r1["vbo_offset"][k]), int(r2["vbo_offset"][k]), int(r1["vbo_items"][k]) * 2
+                assert np.array_equal(m1[a:a + nb], m2[b:b + nb])
+                a, b, nb = int(r1["ibo_offset"][k]), int(r2["ibo_offset"][k]), int(r1["ibo_items"][k]) * 4
+                assert np.array_equal(m1[a:a + nb], m2[b:b + nb])
+        finally:
+            ctx.close()
