@@ -66,6 +66,17 @@ __device__ __forceinline__ uint32_t nz16x128(uint4 v)
 	b = __dp4a(nzflags(v.w), 0x80402010u, b);
 	return a + (b << 8);
 }
+// Bulk copy shared -> global (bytes % 16 == 0, both addresses 16 B aligned), tracked by the thread's bulk async-group.
+__device__ __forceinline__ void bulk_store(void *gdst, const void *smem_src, uint32_t bytes)
+{
+	asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// wait until the committed bulk copies have READ their shared-memory source (it may then be reused / the CTA may exit)
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// make generic-proxy writes to shared memory visible to the async proxy (bulk copies)
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 // L2 prefetch of a byte range (no shared-memory destination, no completion tracking).
 __device__ __forceinline__ void l2_prefetch(const void *gsrc, uint32_t bytes)
 {

@@ -97,7 +97,7 @@ template <int RB> struct Geo {
 	static constexpr int OFF_MISC = OFF_BARS + (2 * RING + 2) * 8;
 	// group record: [NG + 1] exclusive splat prefix, [1] number of non-empty groups, [NG bytes] their indices
 	static constexpr int GP_WORDS = NG + 2 + (NG + 3) / 4;
-	static constexpr int SMEM = OFF_MISC + GP_WORDS * 4 + 16;
+	static constexpr int SMEM = OFF_MISC + 32 + GP_WORDS * 4 + 16;
 	// per-slab scratch in global memory between the count and the emit kernel (16-byte multiples for bulk copies)
 	static constexpr int GP_STRIDE = (GP_WORDS + 3) / 4 * 4;            // uint32 words
 	// emit kernel: level bit arrays | select table | group prefixes | barrier + scalars
@@ -112,6 +112,7 @@ constexpr int kChunkRec = 8;        // uint64 per chunk record
 constexpr int kSlabRec = 16;        // uint32 per slab record: [0..4] counts, [8..12] first splat of the slab's part of level l
 
 struct Misc {                       // count kernel: small per-CTA area in shared memory
+	const uint8_t *src[4];          // own voxels / +x face plane / +y voxels / +z voxels of the chunk (null = null chunk)
 	uint32_t gpre[1];               // [NG + 1] exclusive prefix of the per-group splat counts (extends past the struct)
 };
 
@@ -354,25 +355,6 @@ __host__ __device__ __forceinline__ SplatScratch carve_scratch(uint8_t *base, si
 	return sc;
 }
 
-// Chunk geometry shared by the count and the emit kernel.
-template <int RB> struct ChunkRefs {
-	int cx, cy, cz;
-	const uint8_t *own, *nbx_xlo, *nby, *nbz;
-	__device__ __forceinline__ ChunkRefs(const VpWorldDev &w, uint32_t cid)
-	{
-		constexpr int R = 1 << RB;
-		cx = (int)(cid & ((1u << w.bits[0]) - 1)); cy = (int)((cid >> w.bits[0]) & ((1u << w.bits[1]) - 1));
-		cz = (int)(cid >> (w.bits[0] + w.bits[1]));
-		const int s_own = chunk_slot(w, cx, cy, cz), s_x = chunk_slot(w, cx + 1, cy, cz);
-		const int s_y = chunk_slot(w, cx, cy + 1, cz), s_z = chunk_slot(w, cx, cy, cz + 1);
-		const size_t N = (size_t)R * R * R;
-		own = s_own >= 0 ? w.vox_pool + (size_t)s_own * N : nullptr;
-		nbx_xlo = s_x >= 0 ? w.xlo_pool + (size_t)s_x * R * R : nullptr;
-		nby = s_y >= 0 ? w.vox_pool + (size_t)s_y * N : nullptr;
-		nbz = s_z >= 0 ? w.vox_pool + (size_t)s_z * N : nullptr;
-	}
-};
-
 // End of a slab's count pass: the LAST slab of a chunk to get here (per-chunk arrival counter) adds up the level
 // counts of all slabs, reserves the chunk's contiguous [L0|L1|L2|L3|L4] buffer in the arena with one atomicAdd, and
 // writes the per-slab level bases and the result record (ChunkMD.svl_items[], chunkset.c:469-483).  Nobody waits.
@@ -459,33 +441,37 @@ k_splat_count(const VpWorldDev w, const uint32_t *__restrict__ ids, uint32_t n, 
 	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 	const int crank = CL > 1 ? (int)(blockIdx.x % CL) : 0;
 	const uint32_t chunk_i = blockIdx.x / CL;
-	const ChunkRefs<RB> ch(w, ids[chunk_i]);
-	const uint8_t *own = ch.own, *nbx_xlo = ch.nbx_xlo, *nby = ch.nby, *nbz = ch.nbz;
 	const int z0 = crank * ZS;
 	const bool top = (z0 + ZS == R);
 	const SplatScratch sc = carve_scratch<RB>(scratch, arrived_bytes, n);
 	uint32_t *rec = sc.rec + (size_t)blockIdx.x * kSlabRec;
-
 	VpResultDev *res = results + (result_pos ? result_pos[chunk_i] : chunk_i);
-	if (crank == 0 && tid < 4) {                      // the emit kernel takes the chunk's source pointers from here
-		const uint8_t *ptr = tid == 0 ? own : (tid == 1 ? nbx_xlo : (tid == 2 ? nby : nbz));
-		sc.chrec[(size_t)chunk_i * kChunkRec + 1 + tid] = (unsigned long long)ptr;
-	}
-	if (!own && !nbx_xlo && !nby && !nbz) {           // mesher.c:404-409: nothing can be visible
-		if (tid < 5) rec[tid] = 0;
-		chunk_reserve<CL>(sc, chunk_i, res, st);
-		return;
-	}
 
 	VP_PHASE_INIT;
-	// ---- phase 0: barriers, zero the bit arrays ---------------------------------------------------
-	if (tid == 0) {
+	// ---- phase 0: source pointers (4 threads, one slot lookup each), barriers, zeroed bit arrays -------
+	if (tid < 4) {
+		const uint32_t cid = ids[chunk_i];
+		const int cx = (int)(cid & ((1u << w.bits[0]) - 1)), cy = (int)((cid >> w.bits[0]) & ((1u << w.bits[1]) - 1));
+		const int cz = (int)(cid >> (w.bits[0] + w.bits[1]));
+		const int sl = chunk_slot(w, cx + (tid == 1), cy + (tid == 2), cz + (tid == 3));
+		const uint8_t *ptr = nullptr;
+		if (sl >= 0) ptr = tid == 1 ? w.xlo_pool + (size_t)sl * R * R : w.vox_pool + (size_t)sl * R * R * R;
+		misc->src[tid] = ptr;
+		if (crank == 0) sc.chrec[(size_t)chunk_i * kChunkRec + 1 + tid] = (unsigned long long)ptr;       // for the emit kernel
+	}
+	if (tid == 32) {
 		for (int i = 0; i < kRing; i++) { mbar_init(bar_full + i, 1); mbar_init(bar_empty + i, kConsumerWarps / kRing); }
 		mbar_init(bar_halo, 1);
 		mbar_fence_init();
 	}
 	for (int i = tid; i < G::OCC_WORDS + G::OCCX_WORDS; i += kThreads) occ[i] = 0;      // occ, occx are contiguous
 	__syncthreads();
+	const uint8_t *own = misc->src[0], *nbx_xlo = misc->src[1], *nby = misc->src[2], *nbz = misc->src[3];
+	if (!own && !nbx_xlo && !nby && !nbz) {           // mesher.c:404-409: nothing can be visible
+		if (tid < 5) rec[tid] = 0;
+		chunk_reserve<CL>(sc, chunk_i, res, st);
+		return;
+	}
 
 	// source of streamed slice s (z = z0 - 1 + s); nullptr = air or not needed
 	auto slice_src = [&](int s) -> const uint8_t * {
@@ -614,6 +600,13 @@ k_splat_count(const VpWorldDev w, const uint32_t *__restrict__ ids, uint32_t n, 
 		const int f = f0 + lane, zi = f >> RB, y = f & (R - 1), s = zi + 1;
 		const uint64_t *o = occ + (size_t)(s * (R + 1) + y) * NW;
 		const uint64_t xbit = (occx[zi * NW + (y >> 6)] >> (y & 63)) & 1ull;
+		// 32 rows of air with no solid +x halo cell: nothing of them is visible and lv0 is pre-zeroed
+		{
+			uint64_t any = xbit;
+			#pragma unroll
+			for (int k = 0; k < NW; k++) any |= o[k];
+			if (!__any_sync(0xffffffffu, any != 0ull)) continue;
+		}
 		#pragma unroll
 		for (int k = 0; k < NW; k++) {
 			const uint64_t ow = o[k];
@@ -731,16 +724,19 @@ k_splat_count(const VpWorldDev w, const uint32_t *__restrict__ ids, uint32_t n, 
 		}
 		if (lane == 0) gpre[G::NG + 1] = nne;
 	}
+	fence_proxy_async_smem();          // every thread: its writes to the bit arrays become visible to the bulk-copy engine
 	__syncthreads();
 	VP_PHASE(4);
 	// ---- phase 5: bit arrays + group prefixes to the scratch (skipped when nothing is visible) -------
-	if (gpre[G::NG] != 0) {
-		uint64_t *dp = sc.pyr + (size_t)blockIdx.x * G::LV_STRIDE;
-		for (int i = tid; i < G::LV_STRIDE; i += kThreads) dp[i] = lv[i];
-		uint32_t *dg = sc.gp + (size_t)blockIdx.x * G::GP_STRIDE;
-		for (int i = tid; i < G::GP_WORDS; i += kThreads) dg[i] = gpre[i];
+	if (gpre[G::NG] != 0 && tid == 0) {
+		// two bulk copies shared -> global; the copy engine reads shared memory while the CTA goes on to the
+		// reservation, thread 0 waits for those reads before it exits
+		bulk_store(sc.pyr + (size_t)blockIdx.x * G::LV_STRIDE, lv, G::LV_STRIDE * 8);
+		bulk_store(sc.gp + (size_t)blockIdx.x * G::GP_STRIDE, gpre, G::GP_STRIDE * 4);
+		bulk_commit();
 	}
 	chunk_reserve<CL>(sc, chunk_i, res, st);
+	if (tid == 0) bulk_wait_read();
 	VP_PHASE(5);
 }
 
