@@ -789,7 +789,8 @@ k_splat_emit(const VpWorldDev w, const uint32_t *__restrict__ ids, uint32_t n, c
 	            reinterpret_cast<const uint8_t *>(chrec[3]), reinterpret_cast<const uint8_t *>(chrec[4]), z0, ccx << RB, ccy << RB, ccz << RB};
 	uint2 *out2 = reinterpret_cast<uint2 *>(arena + choff);
 	__syncthreads();
-	mbar_wait(&misc->bar, 0);
+	if (tid < 32) mbar_wait(&misc->bar, 0);               // one warp polls the bulk copies, the others sleep in the barrier
+	__syncthreads();
 
 	// Slot s of a group belongs to the unit i with p_i <= s < p_i + c_i (shuffle binary search over the lanes'
 	// exclusive prefixes) and inside the unit to its (s - p_i)-th set bit (popc select): every lane emits one splat
