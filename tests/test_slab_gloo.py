@@ -18,6 +18,7 @@ class HostStore:
     def __init__(self, rank, nbytes):
         self.rank, self.nbytes = rank, nbytes
         self.ghost = {}
+        self.log = []
 
     def halo_plane_bytes(self):
         return self.nbytes
@@ -33,6 +34,11 @@ class HostStore:
     def halo_unpack(self, which, ptr):
         buf = (np.ctypeslib.as_array((__import__("ctypes").c_uint8 * self.nbytes).from_address(ptr)))
         self.ghost[which] = buf.copy()
+        self.log.append(("unpack", which))
+
+    def rebuild_device_part(self, part):
+        # the overlapped step: part 0 must be issued before any plane is unpacked, part 1 after all of them
+        self.log.append(("part", part))
 
 
 def _worker(rank, world_size, port, mesh, out):
@@ -44,6 +50,12 @@ def _worker(rank, world_size, port, mesh, out):
     rb = slab.SlabRebuilder(store, rank, world_size, lambda k: torch.empty(k, dtype=torch.uint8), dist=dist)
     ops = rb.exchange_halos(mesh=mesh)
     ok = True
+    first = dict(store.ghost)
+    store.ghost.clear(); store.log.clear()
+    rb.rebuild_step(mesh=mesh)                       # same planes again, with the rebuild parts around the unpack
+    ok &= set(store.ghost) == set(first) and all(np.array_equal(store.ghost[k], first[k]) for k in first)
+    kinds = [e for e in store.log]
+    ok &= kinds[0] == ("part", 0) and kinds[-1] == ("part", 1) and all(k[0] == "unpack" for k in kinds[1:-1])
     # +z halo: plane 0 of the rank above; -z halo (mesh only): plane 1 of the rank below
     if rank < world_size - 1:
         ok &= 0 in store.ghost and np.array_equal(store.ghost[0], HostStore.plane(rank + 1, 0, n))
