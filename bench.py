@@ -266,17 +266,28 @@ def run_native(args):
     nx, ny, nz = (1 << b for b in bits)
     R, N = 1 << ROOT_BITW, 1 << (3 * ROOT_BITW)
     z0, z1 = slab.slab_rows(nz, world_size, rank)
-    own_ids, dense, solid, shadow_rows, sz0 = generate_slab(bits, z0, z1)
-    nn = np.nonzero(solid)[0]
-
-    own_vox = len(own_ids) * N
+    per_row = nx * ny
+    own_vox = (z1 - z0) * per_row * N
     ctx = vpb.Context(ROOT_BITW, bits, device=local_rank, slab=(z0, z1), splat_arena_bytes=max(2 << 30, own_vox // 2),
                       mesh_arena_bytes=2 << 30, rle_arena_bytes=max(1 << 30, own_vox // 4))
     stream = torch.cuda.Stream()
     ctx.set_stream(stream.cuda_stream)
-    pinned_dense = torch.from_numpy(np.ascontiguousarray(dense[nn])).pin_memory()
-    ctx.upload_chunks_dense(own_ids[nn], pinned_dense)
-    ctx.upload_shadow_rows(sz0, shadow_rows)
+    if WORKLOAD == "c2":
+        own_ids, dense, solid, shadow_rows, sz0 = generate_slab(bits, z0, z1)
+        nn = np.nonzero(solid)[0]
+        pinned_dense = torch.from_numpy(np.ascontiguousarray(dense[nn])).pin_memory()
+        ctx.upload_chunks_dense(own_ids[nn], pinned_dense)
+        ctx.upload_shadow_rows(sz0, shadow_rows)
+        del dense, pinned_dense
+    else:
+        # the big fixed worlds (34 / 137 Gvoxel) are generated on the device: same generator, byte for byte
+        # (tests/test_gpu_worldgen.py), no host generation or upload of tens of GB per rank
+        own_ids = np.arange(z0 * per_row, z1 * per_row, dtype=np.uint32)
+        ctx.generate_world(SEED)
+        solid = ctx.chunks_resident(own_ids).astype(np.uint32)
+        nn = np.nonzero(solid)[0]
+        sz0 = z0 * R
+        shadow_rows = ctx.download_shadow_rows(sz0, min(nz * R, z1 * R + 17))
 
     with torch.cuda.stream(stream):
         rebuilder = slab.SlabRebuilder(ctx, rank, world_size, lambda n: torch.empty(n, dtype=torch.uint8, device="cuda"), dist=dist)

@@ -115,6 +115,10 @@ VP_API int  vp_upload_chunks_dense(vp_ctx *ctx, const uint32_t *chunk_ids, uint3
 VP_API int  vp_upload_chunks_rle(vp_ctx *ctx, const uint32_t *chunk_ids, uint32_t n,
                           const uint32_t *words, const uint64_t *word_offsets);
 
+/* resident[i] = 1 when the chunk holds voxels on the device, 0 when it is the null chunk (the reference's test is
+ * `c->rle == set->null_chunk->rle`, chunkset.c:144-145).  Host-side table lookup, no device work. */
+VP_API int  vp_chunks_resident(vp_ctx *ctx, const uint32_t *chunk_ids, uint32_t n, uint8_t *resident);
+
 /* Make chunks the null chunk (chunkset_clear, chunkset.c:116-117). */
 VP_API int  vp_set_chunks_null(vp_ctx *ctx, const uint32_t *chunk_ids, uint32_t n);
 

@@ -74,6 +74,7 @@ def load_library():
         "vp_upload_chunks_dense": (C.c_int, [vp, vp, C.c_uint32, vp]),
         "vp_upload_chunks_rle": (C.c_int, [vp, vp, C.c_uint32, vp, vp]),
         "vp_set_chunks_null": (C.c_int, [vp, vp, C.c_uint32]),
+        "vp_chunks_resident": (C.c_int, [vp, vp, C.c_uint32, vp]),
         "vp_download_chunks_dense": (C.c_int, [vp, vp, C.c_uint32, vp]),
         "vp_encode_chunks_rle": (C.c_int, [vp, vp, C.c_uint32, vp, C.c_uint64, vp]),
         "vp_upload_shadow_rows": (C.c_int, [vp, C.c_uint32, C.c_uint32, vp]),
@@ -203,6 +204,13 @@ class Context:
                 continue
             self._ck(rc)
             return words[:int(offs[-1])], offs
+
+    def chunks_resident(self, ids):
+        """Boolean array: True where the chunk holds voxels on the device (False = null chunk)."""
+        ids = _u32(ids)
+        out = np.zeros(len(ids), np.uint8)
+        self._ck(self.lib.vp_chunks_resident(self.h, _ptr(ids), len(ids), _ptr(out)))
+        return out.astype(bool)
 
     def generate_world(self, seed):
         """Generate the slab's chunks and height-map rows on the device (same world as worldgen.World(seed, ...))."""

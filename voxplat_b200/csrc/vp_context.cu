@@ -398,6 +398,18 @@ extern "C" int vp_generate_world(vp_ctx *c, uint32_t seed)
 	return VP_OK;
 }
 
+// resident[i] = 1 when chunk ids[i] holds voxels on the device, 0 for the null chunk (chunkset.c:116-117, :225-228).
+extern "C" int vp_chunks_resident(vp_ctx *c, const uint32_t *ids, uint32_t n, uint8_t *resident)
+{
+	if (!c || (n && (!ids || !resident))) return vp_fail(c, VP_ERR_ARG, "vp_chunks_resident: null argument");
+	for (uint32_t i = 0; i < n; i++) {
+		const int64_t e = ext_index(c, ids[i]);
+		if (e < 0) return vp_fail(c, VP_ERR_NOT_RESIDENT, "chunk id outside this context's slab");
+		resident[i] = c->h_slot[(size_t)e] >= 0;
+	}
+	return VP_OK;
+}
+
 extern "C" int vp_set_chunks_null(vp_ctx *c, const uint32_t *ids, uint32_t n)
 {
 	if (!c || (n && !ids)) return vp_fail(c, VP_ERR_ARG, "vp_set_chunks_null: null argument");
