@@ -153,6 +153,8 @@ template <int RB> struct Ctx {
 	const uint8_t *own, *nbx_xlo, *nby, *nbz;     // chunk bytes (may be null)
 	int z0;
 	uint32_t ox, oy, oz;            // chunk origin in world voxels
+	const uint8_t *own_z, *nby_z;   // own / +y neighbour voxels at the slab's first slice
+	uint32_t xo_z;                  // offset of the slab's first row in the +x face plane
 
 	__device__ __forceinline__ static uint32_t pair_at(const uint64_t *row, int bit) { return (uint32_t)(row[bit >> 6] >> (bit & 63)) & 3u; }
 
@@ -274,8 +276,11 @@ __device__ __forceinline__ void emit_group(const Ctx<RB> &cx, const uint64_t *lv
 	const uint8_t *row = nullptr; uint32_t xo = 0;
 	if constexpr (L == 0) {
 		if (q < n_main) {
-			row = (Y < R ? cx.own + ((size_t)(cx.z0 + Zloc) * R + Y) * R : cx.nby + (size_t)(cx.z0 + Zloc) * R * R) + xbase;
-			xo = (uint32_t)((cx.z0 + Zloc) * R + Y);
+			// q = Zloc * (R + 1) + Y, so the row's voxel offset inside the slab is (q - Zloc) * R; the slab base pointers
+			// were computed once per CTA
+			const bool yp = Y >= R;
+			row = (yp ? cx.nby_z : cx.own_z) + ((yp ? (uint32_t)Zloc << (2 * RB) : (uint32_t)(q - Zloc) << RB) + (uint32_t)xbase);
+			xo = cx.xo_z + (uint32_t)(q - Zloc);
 		} else {
 			row = cx.nbz + (size_t)Y * R + xbase;
 		}
@@ -786,7 +791,9 @@ k_splat_emit(const VpWorldDev w, const uint32_t *__restrict__ ids, uint32_t n, c
 	const int z0 = crank * ZS;
 	const uint32_t b0 = rec[8], b1 = rec[9], b2 = rec[10], b3 = rec[11], b4 = rec[12];
 	Ctx<RB> cx_{w, lv, reinterpret_cast<const uint8_t *>(chrec[1]), reinterpret_cast<const uint8_t *>(chrec[2]),
-	            reinterpret_cast<const uint8_t *>(chrec[3]), reinterpret_cast<const uint8_t *>(chrec[4]), z0, ccx << RB, ccy << RB, ccz << RB};
+	            reinterpret_cast<const uint8_t *>(chrec[3]), reinterpret_cast<const uint8_t *>(chrec[4]), z0, ccx << RB, ccy << RB, ccz << RB,
+	            reinterpret_cast<const uint8_t *>(chrec[1]) + (size_t)z0 * R * R, reinterpret_cast<const uint8_t *>(chrec[3]) + (size_t)z0 * R * R,
+	            (uint32_t)z0 * R};
 	uint2 *out2 = reinterpret_cast<uint2 *>(arena + choff);
 	__syncthreads();
 	if (tid < 32) mbar_wait(&misc->bar, 0);               // one warp polls the bulk copies, the others sleep in the barrier
