@@ -346,7 +346,7 @@ def run_native(args):
         nn_flags = np.ascontiguousarray(flags[nn])
 
         def e2e_step():
-            ctx.upload_shadow_rows(sz0, pinned_shadow)
+            ctx.upload_shadow_rows_async(sz0, pinned_shadow)        # travels in front of the step on the context stream
             if world_size == 1:
                 return ctx.rebuild_from_rle(own_ids[nn], pinned_words, offs, per_chunk_flags=nn_flags, n_blocks=8)
             ctx.upload_chunks_rle(own_ids[nn], pinned_words, offs)          # rle_decompress of every chunk on the device

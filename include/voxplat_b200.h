@@ -134,6 +134,9 @@ VP_API int  vp_encode_chunks_rle(vp_ctx *ctx, const uint32_t *chunk_ids, uint32_
 /* Shadow map rows [z0,z1) in world voxel rows, (X+Y) uint16 each (shadow.h:26-51).  Rows outside the
  * context's slab (+17 rows of reach) are ignored. */
 VP_API int  vp_upload_shadow_rows(vp_ctx *ctx, uint32_t z0, uint32_t z1, const uint16_t *rows);
+/* The same without waiting for the copy: the rows travel on the context stream in front of whatever is enqueued next
+ * (e.g. vp_rebuild_from_rle).  `rows` must be page-locked memory and stay valid until the next synchronous call. */
+VP_API int  vp_upload_shadow_rows_async(vp_ctx *ctx, uint32_t z0, uint32_t z1, const uint16_t *rows);
 
 /* ---- flat RLE codec: drop-in bodies for rle_compress / rle_decompress (rle.h:7-8) ------------- */
 

@@ -78,6 +78,7 @@ def load_library():
         "vp_download_chunks_dense": (C.c_int, [vp, vp, C.c_uint32, vp]),
         "vp_encode_chunks_rle": (C.c_int, [vp, vp, C.c_uint32, vp, C.c_uint64, vp]),
         "vp_upload_shadow_rows": (C.c_int, [vp, C.c_uint32, C.c_uint32, vp]),
+        "vp_upload_shadow_rows_async": (C.c_int, [vp, C.c_uint32, C.c_uint32, vp]),
         "vp_rle_compress": (C.c_int, [vp, vp, C.c_uint32, vp, C.c_uint32, C.POINTER(C.c_uint32)]),
         "vp_rle_decompress": (C.c_int, [vp, vp, C.c_uint32, vp, C.c_uint32, C.POINTER(C.c_uint32)]),
         "vp_rebuild_batch": (C.c_int, [vp, vp, C.c_uint32, C.c_uint32, vp, vp, C.POINTER(vp), C.POINTER(vp)]),
@@ -232,6 +233,13 @@ class Context:
         shw = ((1 << self.max_bitw[0]) + (1 << self.max_bitw[1])) << self.root_bitw
         assert rows.size % shw == 0
         self._ck(self.lib.vp_upload_shadow_rows(self.h, z0, z0 + rows.size // shw, _ptr(rows)))
+
+    def upload_shadow_rows_async(self, z0, pinned_rows):
+        """No wait for the copy; `pinned_rows` (a pinned torch tensor of uint16 / int16) must outlive the next synchronous call."""
+        shw = ((1 << self.max_bitw[0]) + (1 << self.max_bitw[1])) << self.root_bitw
+        n = pinned_rows.numel()
+        assert n % shw == 0 and pinned_rows.is_pinned()
+        self._ck(self.lib.vp_upload_shadow_rows_async(self.h, z0, z0 + n // shw, _ptr(pinned_rows)))
 
     # ---- flat RLE codec (rle.h:7-8) -----------------------------------------------------------------
     def rle_compress(self, data):

@@ -438,7 +438,7 @@ extern "C" int vp_download_chunks_dense(vp_ctx *c, const uint32_t *ids, uint32_t
 	return VP_OK;
 }
 
-extern "C" int vp_upload_shadow_rows(vp_ctx *c, uint32_t z0, uint32_t z1, const uint16_t *rows)
+static int upload_shadow_rows(vp_ctx *c, uint32_t z0, uint32_t z1, const uint16_t *rows, bool wait)
 {
 	if (!c || !rows || z1 < z0) return vp_fail(c, VP_ERR_ARG, "vp_upload_shadow_rows: bad argument");
 	VP_CUDA(c, cudaSetDevice(c->cfg.device));
@@ -447,9 +447,12 @@ extern "C" int vp_upload_shadow_rows(vp_ctx *c, uint32_t z0, uint32_t z1, const 
 	if (a < b)
 		VP_CUDA(c, cudaMemcpyAsync(c->d_shadow + (size_t)(a - c->sh_z0) * shw, rows + (size_t)(a - z0) * shw,
 		                           (size_t)(b - a) * shw * sizeof(uint16_t), cudaMemcpyHostToDevice, c->stream));
-	VP_CUDA(c, cudaStreamSynchronize(c->stream));
+	if (wait) VP_CUDA(c, cudaStreamSynchronize(c->stream));
 	return VP_OK;
 }
+
+extern "C" int vp_upload_shadow_rows(vp_ctx *c, uint32_t z0, uint32_t z1, const uint16_t *rows) { return upload_shadow_rows(c, z0, z1, rows, true); }
+extern "C" int vp_upload_shadow_rows_async(vp_ctx *c, uint32_t z0, uint32_t z1, const uint16_t *rows) { return upload_shadow_rows(c, z0, z1, rows, false); }
 
 // ------------------------------------------------------------------------------------------------
 // rebuild
