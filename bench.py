@@ -341,17 +341,27 @@ def run_native(args):
         pinned_shadow = torch.from_numpy(np.ascontiguousarray(shadow_rows)).pin_memory()
         e2e_steps = max(3, min(args.steps, 10))
 
-        # N = 1: one pipelined call (upload+decode | kernels | download overlap over 8 blocks of chunk rows).
-        # N > 1: the border exchange sits between decode and rebuild, so the three calls stay separate.
+        # One pipelined call (upload+decode | kernels | download overlap over 8 blocks of chunk rows).  N > 1: the slab's
+        # first and last chunk rows are decoded first so that the border planes can be exchanged before the pipeline
+        # starts (the pipeline decodes them again with their blocks: 2 of 32 rows).
         nn_flags = np.ascontiguousarray(flags[nn])
+        nn_ids = own_ids[nn]
+        border = None
+        if world_size > 1:
+            rows_of = nn_ids // per_row
+            sel = np.nonzero((rows_of == z0) | (rows_of == z1 - 1))[0]
+            b_words = np.concatenate([words[int(offs[i]):int(offs[i + 1])] for i in sel]) if len(sel) else np.zeros(0, np.uint32)
+            b_offs = np.zeros(len(sel) + 1, np.uint64)
+            b_offs[1:] = np.cumsum([int(offs[i + 1] - offs[i]) for i in sel])
+            border = (np.ascontiguousarray(nn_ids[sel]), torch.from_numpy(b_words).pin_memory(), b_offs)
 
         def e2e_step():
             ctx.upload_shadow_rows_async(sz0, pinned_shadow)        # travels in front of the step on the context stream
-            if world_size == 1:
-                return ctx.rebuild_from_rle(own_ids[nn], pinned_words, offs, per_chunk_flags=nn_flags, n_blocks=8)
-            ctx.upload_chunks_rle(own_ids[nn], pinned_words, offs)          # rle_decompress of every chunk on the device
-            rebuilder.exchange_halos(mesh=True)
-            return ctx.rebuild_batch(own_ids, per_chunk_flags=flags)        # results land in pinned host staging
+            if border is not None:
+                if len(border[0]):
+                    ctx.upload_chunks_rle(*border)                  # rle_decompress of the border rows on the device
+                rebuilder.exchange_halos(mesh=True)
+            return ctx.rebuild_from_rle(nn_ids, pinned_words, offs, per_chunk_flags=nn_flags, n_blocks=8)
 
         for _ in range(3):
             r_e, sb_e, mb_e = e2e_step()
@@ -368,6 +378,8 @@ def run_native(args):
             dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
         e2e_launches = (ctx.kernel_launches() - l0) // e2e_steps
         h2d = int(words.nbytes + offs.nbytes + pinned_shadow.numel() * 2 + own_ids[nn].nbytes + own_ids.nbytes + flags.nbytes)
+        if border is not None:
+            h2d += int(border[1].numel() * 4 + border[2].nbytes + border[0].nbytes)
         d2h = int(sb_e.nbytes + mb_e.nbytes + r_e.nbytes)
 
     # ---- reduce the per-rank figures ----
@@ -418,7 +430,7 @@ def run_native(args):
             "e2e": {"value": e2e_value, "unit": "Gvoxel/s", "h2d_bytes_per_step": int(agg[4].item()), "d2h_bytes_per_step": int(agg[5].item()),
                     "ms_per_step": float(e2e_s.item()) / e2e_steps * 1e3, "steps": e2e_steps,
                     "path": ("host RLE streams (pinned) -> vp_rebuild_from_rle (8 blocks pipelined: H2D + device decode | cull/LOD/splat/mesh | D2H) -> pinned host staging"
-                             if world_size == 1 else "host RLE streams (pinned) -> vp_upload_chunks_rle -> NCCL border exchange -> vp_rebuild_batch -> pinned host staging"),
+                             if world_size == 1 else "host RLE streams (pinned) -> border rows: vp_upload_chunks_rle + NCCL plane exchange -> vp_rebuild_from_rle (8 blocks pipelined) -> pinned host staging"),
                     "gpu_launches_per_step": int(e2e_launches)},
             "gpu_launches": int(launches),
             "clocks": clocks,

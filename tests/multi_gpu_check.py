@@ -41,12 +41,40 @@ def main():
             rbld = slab.SlabRebuilder(ctx, rank, ws, lambda n: torch.empty(n, dtype=torch.uint8, device="cuda"), dist=dist)
             rbld.exchange_halos(mesh=True)
             res, splat, mesh = ctx.rebuild_batch(own, vpb.VP_REBUILD_SPLAT | vpb.VP_REBUILD_MESH)
+            splat, mesh = splat.copy(), mesh.copy()                 # the staging is reused by the later calls
             # the device-resident step with the exchange hidden behind the chunks that do not read a ghost row must
             # give the same buffers (arena offsets may differ: compare per chunk)
             ctx.batch_prepare(own, vpb.VP_REBUILD_SPLAT | vpb.VP_REBUILD_MESH)
             rbld.rebuild_step(mesh=True)
             res2, sb2, mb2 = ctx.rebuild_device_results()
             splat2, mesh2 = ctx.arena_download(0, sb2), ctx.arena_download(1, mb2)
+            # end-to-end form of a slab: border rows decoded first, planes exchanged, then the pipelined call
+            if len(nn):
+                words, offs = ctx.encode_chunks_rle(nn)
+                ctx.set_chunks_null(own)                                # forget the world: everything comes back from RLE
+                rows_of = nn // per_row
+                sel = np.nonzero((rows_of == z0) | (rows_of == z1 - 1))[0]
+                if len(sel):
+                    bw = np.concatenate([words[int(offs[i]):int(offs[i + 1])] for i in sel])
+                    bo = np.zeros(len(sel) + 1, np.uint64)
+                    bo[1:] = np.cumsum([int(offs[i + 1] - offs[i]) for i in sel])
+                    ctx.upload_chunks_rle(np.ascontiguousarray(nn[sel]), bw, bo)
+            rbld.exchange_halos(mesh=True)
+            if len(nn):
+                nn_pos = np.searchsorted(own, nn)
+                res3, splat3, mesh3 = ctx.rebuild_from_rle(nn, words, offs, flags=vpb.VP_REBUILD_SPLAT | vpb.VP_REBUILD_MESH, n_blocks=4)
+                for j, k in enumerate(nn_pos):
+                    ok3 = np.array_equal(res3["svl_items"][j], res["svl_items"][k]) and res3["vbo_items"][j] == res["vbo_items"][k]
+                    if ok3:
+                        a, b, nb = int(res["svl_offset"][k]), int(res3["svl_offset"][j]), int(res["svl_items_total"][k]) * 2
+                        ok3 = np.array_equal(splat[a:a + nb], splat3[b:b + nb])
+                        a, b, nb = int(res["vbo_offset"][k]), int(res3["vbo_offset"][j]), int(res["vbo_items"][k]) * 2
+                        ok3 = ok3 and np.array_equal(mesh[a:a + nb], mesh3[b:b + nb])
+                        a, b, nb = int(res["ibo_offset"][k]), int(res3["ibo_offset"][j]), int(res["ibo_items"][k]) * 4
+                        ok3 = ok3 and np.array_equal(mesh[a:a + nb], mesh3[b:b + nb])
+                    if not ok3:
+                        failures += 1
+                        print("rank %d: chunk %d of world rb=%d %s: pipelined slab e2e differs" % (rank, nn[j], rb, bits), flush=True)
         for k in range(len(own)):
             same = np.array_equal(res2["svl_items"][k], res["svl_items"][k]) and res2["vbo_items"][k] == res["vbo_items"][k] and res2["ibo_items"][k] == res["ibo_items"][k]
             if same:
