@@ -245,6 +245,22 @@ def run_reference(args):
 # ---------------------------------------------------------------------------------------------------
 # native arm
 # ---------------------------------------------------------------------------------------------------
+def bind_to_gpu_numa_node(device_index):
+    """Multi-rank runs: pin this process to the CPUs NVML reports as local to its GPU, so the pinned staging buffers
+    (hundreds of MB per step over PCIe) are allocated on that socket instead of all on node 0.  Best effort."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = [64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1]
+        cpus = [c for c in cpus if c < os.cpu_count()]
+        if cpus and len(cpus) < os.cpu_count():
+            os.sched_setaffinity(0, cpus)
+    except Exception:
+        pass
+
+
 def run_native(args):
     import torch
     import voxplat_b200 as vpb
@@ -259,6 +275,7 @@ def run_native(args):
     torch.cuda.set_device(local_rank)
     dist = None
     if world_size > 1:
+        bind_to_gpu_numa_node(local_rank)       # before any pinned allocation: first touch decides the NUMA node
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
