@@ -1,26 +1,27 @@
-// vp_splat.cu -- cull + 5-level LOD + splat-list emission for a batch of chunks, one kernel.
+// vp_splat.cu -- cull + 5-level LOD + splat-list emission for a batch of chunks: two kernels, no communication between
+// CTAs.
 //
 // Replaces, byte for byte, the splat branch of the reference dispatcher (chunkset.c:371-458):
 //   chunk_make_mask (mesher.c:377-456) -> chunk_make_splatlist level 0 (mesher.c:497-536)
 //   -> 4 x { chunk_mask_downsample (mesher.c:460-493) ; chunk_make_splatlist }
 //
-// Work decomposition: one thread-block CLUSTER per chunk, one CTA per 16-slice
-// z-slab of the chunk (cluster size R/16 = 1/2/4/8).  Each CTA
-//   1. streams its slab (+ the slice below and above) through a ring of shared-memory tiles with 1-D TMA
-//      bulk copies (cp.async.bulk + mbarrier), plus the +x / +y halo bytes of the neighbour chunks;
-//   2. packs bytes into 64-bit occupancy rows (bit x of row (z,y));
-//   3. derives the visibility rows with shift / AND-NOT face tests, then the 4 LOD levels by
-//      pair-OR-compress of the bit rows -- no byte mask is ever materialised;
-//   4. counts rows with popc, block-scans the counts (stable z,y,x order), exchanges the 5 per-level
-//      counts with the other CTAs of the cluster through distributed shared memory, reserves the
-//      chunk's contiguous [L0|L1|L2|L3|L4] buffer in the arena with one atomicAdd per chunk;
-//   5. emits: position from the bit index, colour byte gathered from L2 (for LOD>=1 the colour of the
-//      "last non-zero child in scan order", found by descending the bit pyramids), shadow bit from
-//      two uint16 loads.
+// k_splat_count -- one CTA per 16-slice z-slab of a chunk:
+//   1. streams the slab (+ the slice below and above) through a ring of shared-memory tiles with 1-D TMA bulk copies
+//      (cp.async.bulk + mbarrier), plus the +x / +y halo bytes of the neighbour chunks;
+//   2. packs bytes into 64-bit occupancy rows (bit x of row (z,y)): SWAR non-zero flags gathered with IDP.4A;
+//   3. derives the visibility rows with shift / AND-NOT face tests, then the 4 LOD levels by pair-OR-compress of the
+//      bit rows -- no byte mask is ever materialised;
+//   4. counts groups of 32 rows with popc + REDUX, scans the group counts (stable z,y,x order comes from prefixes);
+//   5. bulk-copies the bit arrays + group prefixes to a scratch in HBM; the LAST slab of a chunk to finish (arrival
+//      counter) reserves the chunk's contiguous [L0|L1|L2|L3|L4] buffer with one atomicAdd and writes the slab bases.
+// k_splat_emit -- one CTA of 8 warps per slab, 64 warps per SM: fetches the slab's bit arrays with bulk copies; warps take
+//   non-empty groups from a ticket; slot -> unit by popc over the window's start mask, slot -> bit by popc halving + a
+//   table; position from the bit index, colour byte gathered from the voxels (for LOD >= 1 the colour of the "last
+//   non-zero child in scan order", found by descending the bit pyramids), shadow bit from two uint16 loads.
+//
+// The VP_* macros below are tuning hooks (scripts/build_variant.sh); the defaults are the measured best for 64^3 chunks.
 #include "vp_device.cuh"
-#include <cooperative_groups.h>
 #include <cstddef>
-namespace cg = cooperative_groups;
 using namespace vp;
 
 namespace {
