@@ -33,7 +33,7 @@ VpWorldDev vp_world_dev(const vp_ctx *c)
 	w.ez0 = c->ez0; w.ez1 = c->ez1;
 	w.slot = c->d_slot;
 	w.vox_pool = c->vox_pool; w.xlo_pool = c->xlo_pool; w.xhi_pool = c->xhi_pool;
-	w.shadow = c->d_shadow; w.sh_z0 = c->sh_z0;
+	w.shadow = c->d_shadow; w.sh_z0 = c->sh_z0; w.sh_z1 = c->sh_z1;
 	w.sh_w = (uint32_t)((c->nx + c->ny) << c->rb);
 	return w;
 }
@@ -93,7 +93,8 @@ static void ctx_free(vp_ctx *c)
 	cudaFree(c->d_ids); cudaFree(c->d_flags); cudaFree(c->d_splat_ids); cudaFree(c->d_mesh_ids); cudaFree(c->d_results);
 	cudaFree(c->d_splat_pos); cudaFree(c->d_mesh_pos);
 	cudaFree(c->d_splat_arena); cudaFree(c->d_mesh_arena); cudaFree(c->d_rle_arena); cudaFree(c->d_arena_state);
-	cudaFree(c->d_splat_scratch);
+	cudaFree(c->d_splat_stage); cudaFree(c->d_mesh_stage);
+	cudaFree(c->d_splat_scratch); cudaFree(c->d_mesh_scratch);
 	cudaFree(c->d_tmp_slots); cudaFree(c->d_io); cudaFree(c->d_node_arena); cudaFree(c->d_nodes); cudaFreeHost(c->h_node_stage);
 	cudaFreeHost(c->h_results); cudaFreeHost(c->h_arena_state); cudaFreeHost(c->h_splat_stage); cudaFreeHost(c->h_mesh_stage);
 	cudaFreeHost(c->h_io_stage);
@@ -183,8 +184,11 @@ extern "C" int vp_ctx_create(const vp_config *cfg, vp_ctx **out)
 	CK(cudaMalloc(&c->d_splat_arena, c->cfg.splat_arena_bytes));
 	CK(cudaMalloc(&c->d_mesh_arena, c->cfg.mesh_arena_bytes));
 	CK(cudaMalloc(&c->d_rle_arena, c->cfg.rle_arena_bytes));
-	CK(cudaMalloc(&c->d_arena_state, 3 * sizeof(VpArenaDev)));
-	CK(cudaHostAlloc(&c->h_arena_state, 6 * sizeof(VpArenaDev), cudaHostAllocDefault));     // [0..2] readback, [3..5] reset template
+	CK(cudaMalloc(&c->d_splat_stage, c->cfg.splat_arena_bytes));
+	CK(cudaMalloc(&c->d_mesh_stage, c->cfg.mesh_arena_bytes));
+	CK(cudaMalloc(&c->d_arena_state, 5 * sizeof(VpArenaDev)));
+	CK(cudaHostAlloc(&c->h_arena_state, 8 * sizeof(VpArenaDev), cudaHostAllocDefault));     // [0..2] readback, [3..7] reset template
+	memset(c->h_arena_state, 0, 8 * sizeof(VpArenaDev));
 	CK(cudaStreamSynchronize(c->stream));
 #undef CK
 	*out = c;
@@ -469,6 +473,14 @@ __global__ void k_publish_step(const VpArenaDev *__restrict__ d_state, VpArenaDe
 	if (threadIdx.x == 0) *h_ticket = ticket;
 }
 
+// reset template of the two staging arenas (h_arena_state[6], [7] -> d_arena_state[3], [4])
+static void stage_template(vp_ctx *c)
+{
+	for (int a = 6; a < 8; a++) { c->h_arena_state[a].cursor = 0; c->h_arena_state[a].overflow = 0; c->h_arena_state[a].pad = 0; }
+	c->h_arena_state[6].capacity = c->cfg.splat_arena_bytes;
+	c->h_arena_state[7].capacity = c->cfg.mesh_arena_bytes;
+}
+
 static int batch_reserve(vp_ctx *c, uint32_t n)
 {
 	if (n <= c->batch_cap) return VP_OK;
@@ -491,18 +503,22 @@ static int batch_reserve(vp_ctx *c, uint32_t n)
 	return VP_OK;
 }
 
-// Scratch between the count / scan / emit kernels of a splat rebuild of up to n chunks per launch.
-static int splat_scratch_reserve(vp_ctx *c, uint32_t n)
+// Scratch of a splat / mesh rebuild of up to n chunks per launch (per-chunk arrival counters first: they start at zero
+// and the kernels leave them at zero).
+static int scratch_reserve(vp_ctx *c, uint8_t **buf, uint32_t *cap_chunks, uint32_t n, size_t (*bytes_for)(int, uint32_t))
 {
-	if (n <= c->splat_scratch_chunks) return VP_OK;
+	if (n <= *cap_chunks) return VP_OK;
 	VP_CUDA(c, cudaStreamSynchronize(c->stream));
-	cudaFree(c->d_splat_scratch); c->d_splat_scratch = nullptr; c->splat_scratch_chunks = 0;
+	VP_CUDA(c, cudaStreamSynchronize(c->mesh_stream));
+	cudaFree(*buf); *buf = nullptr; *cap_chunks = 0;
 	const uint32_t cap = std::max<uint32_t>(n + n / 8, 64);
-	VP_CUDA(c, cudaMalloc(&c->d_splat_scratch, vp_splat_scratch_bytes(c->rb, cap)));
-	VP_CUDA(c, cudaMemsetAsync(c->d_splat_scratch, 0, (size_t)cap * 4 + 256, c->stream));      // per-chunk arrival counters start at zero
-	c->splat_scratch_chunks = cap;
+	VP_CUDA(c, cudaMalloc(buf, bytes_for(c->rb, cap)));
+	VP_CUDA(c, cudaMemsetAsync(*buf, 0, (size_t)cap * 4 + 256, c->stream));
+	*cap_chunks = cap;
 	return VP_OK;
 }
+static int splat_scratch_reserve(vp_ctx *c, uint32_t n) { return scratch_reserve(c, &c->d_splat_scratch, &c->splat_scratch_chunks, n, vp_splat_scratch_bytes); }
+static int mesh_scratch_reserve(vp_ctx *c, uint32_t n) { return scratch_reserve(c, &c->d_mesh_scratch, &c->mesh_scratch_chunks, n, vp_mesh_scratch_bytes); }
 
 extern "C" int vp_batch_prepare(vp_ctx *c, const uint32_t *ids, uint32_t n, const uint8_t *per_chunk_flags, uint32_t flags)
 {
@@ -556,6 +572,7 @@ extern "C" int vp_batch_prepare(vp_ctx *c, const uint32_t *ids, uint32_t n, cons
 	}
 	c->batch_n = n; c->n_splat = (uint32_t)sid.size(); c->n_mesh = (uint32_t)mid.size();
 	if ((rc = splat_scratch_reserve(c, c->n_splat))) return rc;
+	if ((rc = mesh_scratch_reserve(c, c->n_mesh))) return rc;
 	if (c->n_splat) {
 		VP_CUDA(c, cudaMemcpyAsync(c->d_splat_ids, sid.data(), sid.size() * 4, cudaMemcpyHostToDevice, c->stream));
 		VP_CUDA(c, cudaMemcpyAsync(c->d_splat_pos, spos.data(), spos.size() * 4, cudaMemcpyHostToDevice, c->stream));
@@ -569,6 +586,7 @@ extern "C" int vp_batch_prepare(vp_ctx *c, const uint32_t *ids, uint32_t n, cons
 	c->h_arena_state[3].capacity = c->cfg.splat_arena_bytes;
 	c->h_arena_state[4].capacity = c->cfg.mesh_arena_bytes;
 	c->h_arena_state[5].capacity = c->cfg.rle_arena_bytes;
+	stage_template(c);
 	VP_CUDA(c, cudaStreamSynchronize(c->stream));
 	return VP_OK;
 }
@@ -583,7 +601,8 @@ extern "C" int vp_rebuild_device_part(vp_ctx *c, int part)
 	VP_CUDA(c, cudaSetDevice(c->cfg.device));
 	VpWorldDev w = vp_world_dev(c);
 	if (part == 0) {
-		VP_CUDA(c, cudaMemcpyAsync(c->d_arena_state, c->h_arena_state + 3, 2 * sizeof(VpArenaDev), cudaMemcpyHostToDevice, c->stream));
+		// all five states in one copy ([2], the rle / node state, is set again by its users before every use)
+		VP_CUDA(c, cudaMemcpyAsync(c->d_arena_state, c->h_arena_state + 3, 5 * sizeof(VpArenaDev), cudaMemcpyHostToDevice, c->stream));
 		VP_CUDA(c, cudaMemsetAsync(c->d_results, 0, (size_t)c->batch_n * sizeof(VpResultDev), c->stream));
 		c->ev_k_valid[c->rebuilds % vp_ctx::kHist] = 0;
 		c->rebuilds++;
@@ -602,15 +621,17 @@ extern "C" int vp_rebuild_device_part(vp_ctx *c, int part)
 	if (c->n_mesh) {
 		if (part == 0) VP_CUDA(c, cudaEventRecord(ev[2], ms));
 		if (m1 > m0) {
-			VP_CUDA(c, vp_launch_mesh(w, c->d_mesh_ids + m0, m1 - m0, c->d_results, c->d_mesh_pos + m0, c->d_mesh_arena, c->d_arena_state + 1, ms));
-			c->launches++;
+			VP_CUDA(c, vp_launch_mesh(w, c->d_mesh_ids + m0, m1 - m0, c->d_results, c->d_mesh_pos + m0, c->d_mesh_arena, c->d_arena_state + 1,
+			                          c->d_mesh_scratch, c->mesh_scratch_chunks, ms));
+			c->launches += kMeshLaunches;
 		}
 		if (part == 1) { VP_CUDA(c, cudaEventRecord(ev[3], ms)); valid |= 2; }
 	}
 	if (c->n_splat) {
 		if (part == 0) VP_CUDA(c, cudaEventRecord(ev[0], c->stream));
 		if (s1 > s0) {
-			VP_CUDA(c, vp_launch_splat(w, c->d_splat_ids + s0, s1 - s0, c->d_results, c->d_splat_pos + s0, c->d_splat_arena, c->d_arena_state + 0, c->d_splat_scratch, c->splat_scratch_chunks, c->stream));
+			VP_CUDA(c, vp_launch_splat(w, c->d_splat_ids + s0, s1 - s0, c->d_results, c->d_splat_pos + s0, c->d_splat_arena, c->d_arena_state + 0,
+			                           c->d_splat_stage, c->d_arena_state + 3, c->d_splat_scratch, c->splat_scratch_chunks, c->stream));
 			c->launches += kSplatLaunches;
 		}
 		if (part == 1) { VP_CUDA(c, cudaEventRecord(ev[1], c->stream)); valid |= 1; }
@@ -680,12 +701,16 @@ extern "C" int vp_ctx_resize_arenas(vp_ctx *c, uint64_t splat_bytes, uint64_t me
 	VP_CUDA(c, cudaStreamSynchronize(c->stream));
 	if (splat_bytes && splat_bytes != c->cfg.splat_arena_bytes) {
 		cudaFree(c->d_splat_arena); c->d_splat_arena = nullptr;
+		cudaFree(c->d_splat_stage); c->d_splat_stage = nullptr;
 		VP_CUDA(c, cudaMalloc(&c->d_splat_arena, splat_bytes));
+		VP_CUDA(c, cudaMalloc(&c->d_splat_stage, splat_bytes));
 		c->cfg.splat_arena_bytes = splat_bytes;
 	}
 	if (mesh_bytes && mesh_bytes != c->cfg.mesh_arena_bytes) {
 		cudaFree(c->d_mesh_arena); c->d_mesh_arena = nullptr;
+		cudaFree(c->d_mesh_stage); c->d_mesh_stage = nullptr;
 		VP_CUDA(c, cudaMalloc(&c->d_mesh_arena, mesh_bytes));
+		VP_CUDA(c, cudaMalloc(&c->d_mesh_stage, mesh_bytes));
 		c->cfg.mesh_arena_bytes = mesh_bytes;
 	}
 	return VP_OK;
@@ -1043,9 +1068,10 @@ extern "C" int vp_rebuild_from_rle(vp_ctx *c, const uint32_t *ids, uint32_t n, c
 		s_first[t + 1] = (uint32_t)sid.size(); m_first[t + 1] = (uint32_t)mid.size();
 	}
 	{
-		uint32_t largest = 0;
-		for (uint32_t t = 0; t < n_blocks; t++) largest = std::max(largest, s_first[t + 1] - s_first[t]);
+		uint32_t largest = 0, largest_m = 0;
+		for (uint32_t t = 0; t < n_blocks; t++) { largest = std::max(largest, s_first[t + 1] - s_first[t]); largest_m = std::max(largest_m, m_first[t + 1] - m_first[t]); }
 		if ((rc = splat_scratch_reserve(c, largest))) return rc;
+		if ((rc = mesh_scratch_reserve(c, largest_m))) return rc;
 	}
 	if (!sid.empty()) {
 		VP_CUDA(c, cudaMemcpyAsync(c->d_splat_ids, sid.data(), sid.size() * 4, cudaMemcpyHostToDevice, c->stream));
@@ -1059,7 +1085,8 @@ extern "C" int vp_rebuild_from_rle(vp_ctx *c, const uint32_t *ids, uint32_t n, c
 	for (int a = 0; a < 3; a++) { c->h_arena_state[3 + a].cursor = 0; c->h_arena_state[3 + a].overflow = 0; c->h_arena_state[3 + a].pad = 0; }
 	c->h_arena_state[3].capacity = c->cfg.splat_arena_bytes;
 	c->h_arena_state[4].capacity = c->cfg.mesh_arena_bytes;
-	VP_CUDA(c, cudaMemcpyAsync(c->d_arena_state, c->h_arena_state + 3, 2 * sizeof(VpArenaDev), cudaMemcpyHostToDevice, c->stream));
+	stage_template(c);
+	VP_CUDA(c, cudaMemcpyAsync(c->d_arena_state, c->h_arena_state + 3, 5 * sizeof(VpArenaDev), cudaMemcpyHostToDevice, c->stream));
 	VP_CUDA(c, cudaMemsetAsync(c->d_results, 0, (size_t)n * sizeof(VpResultDev), c->stream));
 	// staging sized from the previous call (grown afterwards if this batch turns out larger)
 	if ((rc = stage_reserve(c, &c->h_splat_stage, &c->splat_stage_cap, std::max<uint64_t>(c->last_splat_bytes + c->last_splat_bytes / 4, 32u << 20)))) return rc;
@@ -1116,12 +1143,14 @@ extern "C" int vp_rebuild_from_rle(vp_ctx *c, const uint32_t *ids, uint32_t n, c
 		VP_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_pipe[0][t], 0));
 		enqueued_steps = t + 1;
 		if (s_first[t + 1] > s_first[t]) {
-			VP_CUDA(c, vp_launch_splat(w, c->d_splat_ids + s_first[t], s_first[t + 1] - s_first[t], c->d_results, c->d_splat_pos + s_first[t], c->d_splat_arena, c->d_arena_state + 0, c->d_splat_scratch, c->splat_scratch_chunks, c->stream));
+			VP_CUDA(c, vp_launch_splat(w, c->d_splat_ids + s_first[t], s_first[t + 1] - s_first[t], c->d_results, c->d_splat_pos + s_first[t], c->d_splat_arena, c->d_arena_state + 0,
+			                           c->d_splat_stage, c->d_arena_state + 3, c->d_splat_scratch, c->splat_scratch_chunks, c->stream));
 			c->launches += kSplatLaunches;
 		}
 		if (m_first[t + 1] > m_first[t]) {
-			VP_CUDA(c, vp_launch_mesh(w, c->d_mesh_ids + m_first[t], m_first[t + 1] - m_first[t], c->d_results, c->d_mesh_pos + m_first[t], c->d_mesh_arena, c->d_arena_state + 1, c->stream));
-			c->launches++;
+			VP_CUDA(c, vp_launch_mesh(w, c->d_mesh_ids + m_first[t], m_first[t + 1] - m_first[t], c->d_results, c->d_mesh_pos + m_first[t], c->d_mesh_arena, c->d_arena_state + 1,
+			                          c->d_mesh_scratch, c->mesh_scratch_chunks, c->stream));
+			c->launches += kMeshLaunches;
 		}
 		k_publish_step<<<1, 32, 0, c->stream>>>(c->d_arena_state, c->h_steps + 2 * t, tickets + t, ticket);
 		VP_CUDA(c, cudaGetLastError());

@@ -39,7 +39,7 @@ k_edit_sphere(VpWorldDev w, uint8_t *__restrict__ vox_pool, uint16_t *__restrict
 	if (!voxel || threadIdx.x >= e) return;
 	const int z = lo[2] + threadIdx.x;
 	if (z < 0 || z >= Z) return;
-	if ((unsigned)z < w.sh_z0) return;
+	if ((unsigned)z < w.sh_z0 || (unsigned)z >= w.sh_z1) return;               // rows this device does not hold (a slab keeps [sh_z0, sh_z1))
 	uint16_t *row = shadow + (size_t)(z - (int)w.sh_z0) * w.sh_w;
 	const int hx = cx + radius + 1, hy = cy + radius + 1;           // exclusive upper corner of the box
 	const int dz = z - cz;

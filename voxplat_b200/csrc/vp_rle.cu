@@ -50,7 +50,7 @@ k_rle_decode(const uint32_t *__restrict__ words, const unsigned long long *__res
 	uint8_t *dst = dst_base + (size_t)(slots ? slots[i] : i) * N;
 	const uint32_t *w = words + offsets[i];
 	const uint32_t nw = (uint32_t)(offsets[i + 1] - offsets[i]) - 1u;       // runs, without the terminator
-	uint32_t widx = 0, wstart = 0, pos = 0;
+	uint32_t widx = 0, wstart = 0, pos = 0, bad = 0;
 	constexpr int IPT = kDecTile / kT;
 	while (widx < nw) {
 		const uint32_t tc = min((uint32_t)kDecTile, nw - widx);
@@ -60,10 +60,13 @@ k_rle_decode(const uint32_t *__restrict__ words, const unsigned long long *__res
 			const uint32_t j = tid * IPT + k;
 			uint32_t word = j < tc ? __ldg(w + widx + j) : 0u;
 			c[k] = word & 0xFFFFFFu;
+			if (c[k] > N) { c[k] = N; bad = 1u; }          // no run of a valid stream is longer than the chunk
 			if (j < tc) s_val[j] = (uint8_t)(word >> 24);
 			sum += c[k];
 		}
-		uint32_t total, pre = block_scan_excl(sum, s_wsum, &total) + wstart;
+		// a thread's 8 runs are worth at most N + 1 to the block scan: the sum of a (malformed) tile then stays far below
+		// 2^32 (256 (N + 1)), and every start offset past the saturation point is > N, i.e. never searched for
+		uint32_t total, pre = block_scan_excl(min(sum, N + 1u), s_wsum, &total) + wstart;
 		#pragma unroll
 		for (int k = 0; k < IPT; k++) { const uint32_t j = tid * IPT + k; if (j <= tc) s_start[j] = pre; pre += c[k]; }
 		if (tid == kT - 1) s_start[tc] = wstart + total;      // (also covers tc == kDecTile)
@@ -85,7 +88,7 @@ k_rle_decode(const uint32_t *__restrict__ words, const unsigned long long *__res
 			uint32_t out[4] = {0, 0, 0, 0};
 			#pragma unroll
 			for (int b = 0; b < 16; b++) {
-				while (o + b >= s_start[k + 1]) k++;
+				while (k + 1 < tc && o + b >= s_start[k + 1]) k++;
 				out[b >> 2] |= (uint32_t)s_val[k] << ((b & 3) * 8);
 			}
 			*reinterpret_cast<uint4 *>(dst + o) = make_uint4(out[0], out[1], out[2], out[3]);
@@ -106,6 +109,7 @@ k_rle_decode(const uint32_t *__restrict__ words, const unsigned long long *__res
 		const uint32_t adv = s_next[0];
 		wstart = s_next[1];
 		widx += adv;
+		if (covered >= N && !last && tid == 0) atomicExch(status, 1u);       // runs left after the chunk is full: stream too long
 		if (covered >= N || last) break;           // a short final tile: the tail below zero-fills and flags the stream
 		if (adv == 0) { if (tid == 0) atomicExch(status, 1u); break; }      // no progress (zero-length runs): malformed
 		__syncthreads();
@@ -113,6 +117,7 @@ k_rle_decode(const uint32_t *__restrict__ words, const unsigned long long *__res
 	// a short stream leaves the tail undefined in the reference; make it deterministic (zeros) and flag it
 	for (uint32_t o = pos + tid * 16; o < N; o += kT * 16) *reinterpret_cast<uint4 *>(dst + o) = make_uint4(0, 0, 0, 0);
 	if (pos < N && tid == 0) atomicExch(status, 1u);
+	if (bad) atomicExch(status, 1u);
 }
 
 // ---- encode ----------------------------------------------------------------------------------------
