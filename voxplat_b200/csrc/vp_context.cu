@@ -93,7 +93,6 @@ static void ctx_free(vp_ctx *c)
 	cudaFree(c->d_ids); cudaFree(c->d_flags); cudaFree(c->d_splat_ids); cudaFree(c->d_mesh_ids); cudaFree(c->d_results);
 	cudaFree(c->d_splat_pos); cudaFree(c->d_mesh_pos);
 	cudaFree(c->d_splat_arena); cudaFree(c->d_mesh_arena); cudaFree(c->d_rle_arena); cudaFree(c->d_arena_state);
-	cudaFree(c->d_splat_stage); cudaFree(c->d_mesh_stage);
 	cudaFree(c->d_splat_scratch); cudaFree(c->d_mesh_scratch);
 	cudaFree(c->d_tmp_slots); cudaFree(c->d_io); cudaFree(c->d_node_arena); cudaFree(c->d_nodes); cudaFreeHost(c->h_node_stage);
 	cudaFreeHost(c->h_results); cudaFreeHost(c->h_arena_state); cudaFreeHost(c->h_splat_stage); cudaFreeHost(c->h_mesh_stage);
@@ -184,11 +183,9 @@ extern "C" int vp_ctx_create(const vp_config *cfg, vp_ctx **out)
 	CK(cudaMalloc(&c->d_splat_arena, c->cfg.splat_arena_bytes));
 	CK(cudaMalloc(&c->d_mesh_arena, c->cfg.mesh_arena_bytes));
 	CK(cudaMalloc(&c->d_rle_arena, c->cfg.rle_arena_bytes));
-	CK(cudaMalloc(&c->d_splat_stage, c->cfg.splat_arena_bytes));
-	CK(cudaMalloc(&c->d_mesh_stage, c->cfg.mesh_arena_bytes));
-	CK(cudaMalloc(&c->d_arena_state, 5 * sizeof(VpArenaDev)));
-	CK(cudaHostAlloc(&c->h_arena_state, 8 * sizeof(VpArenaDev), cudaHostAllocDefault));     // [0..2] readback, [3..7] reset template
-	memset(c->h_arena_state, 0, 8 * sizeof(VpArenaDev));
+	CK(cudaMalloc(&c->d_arena_state, 3 * sizeof(VpArenaDev)));
+	CK(cudaHostAlloc(&c->h_arena_state, 6 * sizeof(VpArenaDev), cudaHostAllocDefault));     // [0..2] readback, [3..5] reset template
+	memset(c->h_arena_state, 0, 6 * sizeof(VpArenaDev));
 	CK(cudaStreamSynchronize(c->stream));
 #undef CK
 	*out = c;
@@ -473,14 +470,6 @@ __global__ void k_publish_step(const VpArenaDev *__restrict__ d_state, VpArenaDe
 	if (threadIdx.x == 0) *h_ticket = ticket;
 }
 
-// reset template of the two staging arenas (h_arena_state[6], [7] -> d_arena_state[3], [4])
-static void stage_template(vp_ctx *c)
-{
-	for (int a = 6; a < 8; a++) { c->h_arena_state[a].cursor = 0; c->h_arena_state[a].overflow = 0; c->h_arena_state[a].pad = 0; }
-	c->h_arena_state[6].capacity = c->cfg.splat_arena_bytes;
-	c->h_arena_state[7].capacity = c->cfg.mesh_arena_bytes;
-}
-
 static int batch_reserve(vp_ctx *c, uint32_t n)
 {
 	if (n <= c->batch_cap) return VP_OK;
@@ -586,7 +575,6 @@ extern "C" int vp_batch_prepare(vp_ctx *c, const uint32_t *ids, uint32_t n, cons
 	c->h_arena_state[3].capacity = c->cfg.splat_arena_bytes;
 	c->h_arena_state[4].capacity = c->cfg.mesh_arena_bytes;
 	c->h_arena_state[5].capacity = c->cfg.rle_arena_bytes;
-	stage_template(c);
 	VP_CUDA(c, cudaStreamSynchronize(c->stream));
 	return VP_OK;
 }
@@ -601,8 +589,7 @@ extern "C" int vp_rebuild_device_part(vp_ctx *c, int part)
 	VP_CUDA(c, cudaSetDevice(c->cfg.device));
 	VpWorldDev w = vp_world_dev(c);
 	if (part == 0) {
-		// all five states in one copy ([2], the rle / node state, is set again by its users before every use)
-		VP_CUDA(c, cudaMemcpyAsync(c->d_arena_state, c->h_arena_state + 3, 5 * sizeof(VpArenaDev), cudaMemcpyHostToDevice, c->stream));
+		VP_CUDA(c, cudaMemcpyAsync(c->d_arena_state, c->h_arena_state + 3, 2 * sizeof(VpArenaDev), cudaMemcpyHostToDevice, c->stream));
 		VP_CUDA(c, cudaMemsetAsync(c->d_results, 0, (size_t)c->batch_n * sizeof(VpResultDev), c->stream));
 		c->ev_k_valid[c->rebuilds % vp_ctx::kHist] = 0;
 		c->rebuilds++;
@@ -631,7 +618,7 @@ extern "C" int vp_rebuild_device_part(vp_ctx *c, int part)
 		if (part == 0) VP_CUDA(c, cudaEventRecord(ev[0], c->stream));
 		if (s1 > s0) {
 			VP_CUDA(c, vp_launch_splat(w, c->d_splat_ids + s0, s1 - s0, c->d_results, c->d_splat_pos + s0, c->d_splat_arena, c->d_arena_state + 0,
-			                           c->d_splat_stage, c->d_arena_state + 3, c->d_splat_scratch, c->splat_scratch_chunks, c->stream));
+			                           c->d_splat_scratch, c->splat_scratch_chunks, c->stream));
 			c->launches += kSplatLaunches;
 		}
 		if (part == 1) { VP_CUDA(c, cudaEventRecord(ev[1], c->stream)); valid |= 1; }
@@ -701,16 +688,12 @@ extern "C" int vp_ctx_resize_arenas(vp_ctx *c, uint64_t splat_bytes, uint64_t me
 	VP_CUDA(c, cudaStreamSynchronize(c->stream));
 	if (splat_bytes && splat_bytes != c->cfg.splat_arena_bytes) {
 		cudaFree(c->d_splat_arena); c->d_splat_arena = nullptr;
-		cudaFree(c->d_splat_stage); c->d_splat_stage = nullptr;
 		VP_CUDA(c, cudaMalloc(&c->d_splat_arena, splat_bytes));
-		VP_CUDA(c, cudaMalloc(&c->d_splat_stage, splat_bytes));
 		c->cfg.splat_arena_bytes = splat_bytes;
 	}
 	if (mesh_bytes && mesh_bytes != c->cfg.mesh_arena_bytes) {
 		cudaFree(c->d_mesh_arena); c->d_mesh_arena = nullptr;
-		cudaFree(c->d_mesh_stage); c->d_mesh_stage = nullptr;
 		VP_CUDA(c, cudaMalloc(&c->d_mesh_arena, mesh_bytes));
-		VP_CUDA(c, cudaMalloc(&c->d_mesh_stage, mesh_bytes));
 		c->cfg.mesh_arena_bytes = mesh_bytes;
 	}
 	return VP_OK;
@@ -1085,8 +1068,7 @@ extern "C" int vp_rebuild_from_rle(vp_ctx *c, const uint32_t *ids, uint32_t n, c
 	for (int a = 0; a < 3; a++) { c->h_arena_state[3 + a].cursor = 0; c->h_arena_state[3 + a].overflow = 0; c->h_arena_state[3 + a].pad = 0; }
 	c->h_arena_state[3].capacity = c->cfg.splat_arena_bytes;
 	c->h_arena_state[4].capacity = c->cfg.mesh_arena_bytes;
-	stage_template(c);
-	VP_CUDA(c, cudaMemcpyAsync(c->d_arena_state, c->h_arena_state + 3, 5 * sizeof(VpArenaDev), cudaMemcpyHostToDevice, c->stream));
+	VP_CUDA(c, cudaMemcpyAsync(c->d_arena_state, c->h_arena_state + 3, 2 * sizeof(VpArenaDev), cudaMemcpyHostToDevice, c->stream));
 	VP_CUDA(c, cudaMemsetAsync(c->d_results, 0, (size_t)n * sizeof(VpResultDev), c->stream));
 	// staging sized from the previous call (grown afterwards if this batch turns out larger)
 	if ((rc = stage_reserve(c, &c->h_splat_stage, &c->splat_stage_cap, std::max<uint64_t>(c->last_splat_bytes + c->last_splat_bytes / 4, 32u << 20)))) return rc;
@@ -1144,7 +1126,7 @@ extern "C" int vp_rebuild_from_rle(vp_ctx *c, const uint32_t *ids, uint32_t n, c
 		enqueued_steps = t + 1;
 		if (s_first[t + 1] > s_first[t]) {
 			VP_CUDA(c, vp_launch_splat(w, c->d_splat_ids + s_first[t], s_first[t + 1] - s_first[t], c->d_results, c->d_splat_pos + s_first[t], c->d_splat_arena, c->d_arena_state + 0,
-			                           c->d_splat_stage, c->d_arena_state + 3, c->d_splat_scratch, c->splat_scratch_chunks, c->stream));
+			                           c->d_splat_scratch, c->splat_scratch_chunks, c->stream));
 			c->launches += kSplatLaunches;
 		}
 		if (m_first[t + 1] > m_first[t]) {

@@ -90,9 +90,8 @@ struct vp_ctx {
 	VpResultDev *d_results; VpResultDev *h_results;      // h_results pinned
 	// arenas
 	uint8_t *d_splat_arena, *d_mesh_arena, *d_rle_arena;
-	uint8_t *d_splat_stage, *d_mesh_stage;   // per-slab staging of the records (same capacity as the arenas)
-	VpArenaDev *d_arena_state;    // [0] splat, [1] mesh, [2] rle / nodes, [3] splat staging, [4] mesh staging
-	VpArenaDev *h_arena_state;    // pinned: [0..2] read-back, [3..7] reset template of the five device states
+	VpArenaDev *d_arena_state;    // [0] splat, [1] mesh, [2] rle / nodes
+	VpArenaDev *h_arena_state;    // pinned: [0..2] read-back, [3..5] reset template
 	uint8_t *h_splat_stage, *h_mesh_stage; size_t splat_stage_cap, mesh_stage_cap;
 	uint8_t *h_io_stage; size_t io_stage_cap;            // pinned staging for uploads / rle
 	uint8_t *d_node_arena; size_t node_arena_cap; VpNodeDev *d_nodes; uint32_t nodes_cap;   // LOD-node aggregation (vp_nodes.cu)
@@ -109,14 +108,12 @@ int vp_fail(vp_ctx *c, int code, const char *what, cudaError_t e = cudaSuccess);
 #define VP_CUDA(ctx, call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return vp_fail(ctx, VP_ERR_CUDA, #call, e__); } while (0)
 
 // kernel launchers (each returns a cudaError_t from the launch)
-// splat rebuild = 1 launch.  Slabs stage their records in `stage` (bump-allocated through stage_state, same
-// capacity as the arena); the last slab of a chunk moves them into the chunk's buffer in `arena`.  scratch was allocated
-// (and zero-filled once) for launches of up to scratch_chunks chunks: vp_*_scratch_bytes(rb, scratch_chunks) bytes.
+// splat rebuild = 2 launches (count + reserve, emit); scratch was allocated (and zero-filled once) for launches of up to
+// scratch_chunks chunks: vp_splat_scratch_bytes(rb, scratch_chunks) bytes
 cudaError_t vp_launch_splat(const VpWorldDev &w, const uint32_t *d_ids, uint32_t n, VpResultDev *d_results, const uint32_t *d_result_pos,
-                            uint8_t *arena, VpArenaDev *state, uint8_t *stage, VpArenaDev *stage_state, uint8_t *scratch,
-                            uint32_t scratch_chunks, cudaStream_t s);
+                            uint8_t *arena, VpArenaDev *state, uint8_t *scratch, uint32_t scratch_chunks, cudaStream_t s);
 size_t vp_splat_scratch_bytes(int rb, uint32_t n);
-constexpr int kSplatLaunches = 1;
+constexpr int kSplatLaunches = 2;
 // mesh rebuild = 2 launches (count + reserve, emit) with the occupancy tiles of the slabs carried through `scratch`
 cudaError_t vp_launch_mesh(const VpWorldDev &w, const uint32_t *d_ids, uint32_t n, VpResultDev *d_results, const uint32_t *d_result_pos,
                            uint8_t *arena, VpArenaDev *state, uint8_t *scratch, uint32_t scratch_chunks, cudaStream_t s);
