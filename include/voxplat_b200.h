@@ -170,6 +170,9 @@ VP_API int  vp_rebuild_from_rle(vp_ctx *ctx, const uint32_t *chunk_ids, uint32_t
 /* Asynchronous device-resident variant (what the bench times as `value`): chunk ids are taken from
  * the host array once (vp_batch_prepare), kernels are enqueued on the context stream, outputs stay
  * in the device arenas.  vp_rebuild_device_results copies the per-chunk records back. */
+/* vp_batch_prepare must be repeated after anything that turns a chunk null or resident (uploads, vp_set_chunks_null,
+ * vp_edit_sphere, vp_generate_world, vp_world_load): the prepared lists leave out chunks that had nothing to show;
+ * vp_rebuild_device fails with VP_ERR_ARG otherwise. */
 VP_API int  vp_batch_prepare(vp_ctx *ctx, const uint32_t *chunk_ids, uint32_t n, const uint8_t *per_chunk_flags,
                       uint32_t flags);
 VP_API int  vp_rebuild_device(vp_ctx *ctx);
@@ -257,10 +260,45 @@ VP_API int  vp_world_file_info(const char *path, int32_t *root_bitw, int32_t max
  * above: its -z halo, needed by mesh AO only).  `device_buf` is a device pointer (e.g. a torch tensor's
  * data_ptr) that NCCL sends/receives; pack/unpack run on the context stream. */
 VP_API uint64_t vp_halo_plane_bytes(vp_ctx *ctx);
+/* The border work of a slab context -- vp_halo_pack, vp_halo_unpack and vp_rebuild_device_part(ctx, 1) -- runs on the
+ * context's border stream (a cudaStream_t returned as void*), beside the interior chunks on the context stream.  The
+ * caller's transport (NCCL send / receive of the packed planes) has to be ordered against THIS stream: after the pack,
+ * before the unpack.  vp_rebuild_device_part(ctx, 1) joins the border stream back into the context stream. */
+VP_API void *vp_ctx_border_stream(vp_ctx *ctx);
 VP_API int  vp_halo_pack(vp_ctx *ctx, int which, void *device_buf);
 /* which: 0 = plane received from the rank ABOVE (becomes z-slice 0 of ghost row slab_z1),
  *        1 = plane received from the rank BELOW (becomes z-slice R-1 of ghost row slab_z0-1). */
 VP_API int  vp_halo_unpack(vp_ctx *ctx, int which, const void *device_buf);
+
+/* ---- several GPUs behind one handle, one host thread (new: the reference is single-device) ------------ */
+
+/* The world is cut into z-slabs of chunk rows, one vp_ctx per device (devices[i], or 0..ndev-1 when devices is NULL;
+ * ndev must divide the chunk rows).  Border planes are written by one kernel per plane straight into the neighbour's
+ * ghost chunks over NVLink (peer access), no NCCL.  This is what the C drop-in for chunkset_manage
+ * (chunkset.c:246-507; voxplat_b200/host/vp_chunkset_manage.c) talks to: every call below is the vp_* call of the same
+ * name routed to the device that owns each chunk. */
+typedef struct vp_multi vp_multi;
+VP_API int32_t vp_device_count(void);                             /* visible CUDA devices (0 when there is none) */
+VP_API int  vp_multi_create(const vp_config *base, const int32_t *devices, int32_t ndev, vp_multi **out);
+VP_API void vp_multi_destroy(vp_multi *m);
+VP_API const char *vp_multi_last_error(const vp_multi *m);       /* m may be NULL for creation errors */
+VP_API int32_t vp_multi_devices(const vp_multi *m);
+VP_API vp_ctx *vp_multi_ctx(vp_multi *m, int32_t i);              /* the i-th slab's context (owned by m) */
+VP_API int32_t vp_multi_owner(const vp_multi *m, uint32_t chunk_id);
+VP_API int  vp_multi_upload_chunks_dense(vp_multi *m, const uint32_t *chunk_ids, uint32_t n, const uint8_t *host_dense);
+VP_API int  vp_multi_upload_chunks_rle(vp_multi *m, const uint32_t *chunk_ids, uint32_t n, const uint32_t *words, const uint64_t *word_offsets);
+VP_API int  vp_multi_set_chunks_null(vp_multi *m, const uint32_t *chunk_ids, uint32_t n);
+VP_API int  vp_multi_upload_shadow_rows(vp_multi *m, uint32_t z0, uint32_t z1, const uint16_t *rows);
+/* Push every slab's border planes into its neighbours' ghost chunks (mesh != 0: also the planes only mesh AO reads). */
+VP_API int  vp_multi_exchange_halos(vp_multi *m, int32_t mesh);
+VP_API int  vp_multi_batch_prepare(vp_multi *m, const uint32_t *chunk_ids, uint32_t n, const uint8_t *per_chunk_flags, uint32_t flags);
+/* One device-resident step on all devices: interior chunks | border planes peer to peer | border chunks.  Asynchronous. */
+VP_API int  vp_multi_rebuild_device(vp_multi *m, int32_t mesh);
+VP_API int  vp_multi_synchronize(vp_multi *m);
+/* vp_rebuild_batch over all devices.  results[i] is relative to splat_bases[owner[i]] / mesh_bases[owner[i]] (arrays of
+ * vp_multi_devices() entries, pinned staging of the owning context, valid until the next rebuild call). */
+VP_API int  vp_multi_rebuild_batch(vp_multi *m, const uint32_t *chunk_ids, uint32_t n, uint32_t flags, const uint8_t *per_chunk_flags,
+                            vp_chunk_result *results, uint8_t *owner, const void **splat_bases, const void **mesh_bases);
 
 #ifdef __cplusplus
 }

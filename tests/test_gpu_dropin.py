@@ -65,7 +65,24 @@ def drain(lib, s, n_chunks, manage):
     raise AssertionError("dispatcher did not drain")
 
 
-def test_chunkset_manage_dropin_matches_reference_dispatcher():
+def slab_device_lists():
+    """"": the dispatcher's own choice (every visible GPU); "0,0": two z-slabs on one device (vp_multi, 1-GPU boxes);
+    "0,1": one slab per device, border planes over NVLink peer access (needs 2 GPUs)."""
+    import torch
+    out = ["", "0,0"]
+    if torch.cuda.is_available() and torch.cuda.device_count() >= 2:
+        out.append("0,1")
+    return out
+
+
+@pytest.mark.parametrize("devices", ["", "0,0", "0,1"])
+def test_chunkset_manage_dropin_matches_reference_dispatcher(devices):
+    if devices not in slab_device_lists():
+        pytest.skip("needs 2 GPUs")
+    if devices:
+        os.environ["VP_DEVICES"] = devices                     # read by the drop-in when it attaches to a new ChunkSet
+    else:
+        os.environ.pop("VP_DEVICES", None)
     lib = load()
     w = worldgen.World(2024, 5, (2, 1, 2))
     mesh_ids = [0, 1, 4, 5]

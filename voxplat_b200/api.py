@@ -101,6 +101,23 @@ def load_library():
         "vp_world_load": (C.c_int, [vp, C.c_char_p]),
         "vp_world_file_info": (C.c_int, [C.c_char_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32 * 3), C.POINTER(C.c_uint64)]),
         "vp_halo_plane_bytes": (C.c_uint64, [vp]),
+        "vp_ctx_border_stream": (vp, [vp]),
+        "vp_device_count": (C.c_int32, []),
+        "vp_multi_create": (C.c_int, [C.POINTER(VpConfig), vp, C.c_int32, C.POINTER(vp)]),
+        "vp_multi_destroy": (None, [vp]),
+        "vp_multi_last_error": (C.c_char_p, [vp]),
+        "vp_multi_devices": (C.c_int32, [vp]),
+        "vp_multi_ctx": (vp, [vp, C.c_int32]),
+        "vp_multi_owner": (C.c_int32, [vp, C.c_uint32]),
+        "vp_multi_upload_chunks_dense": (C.c_int, [vp, vp, C.c_uint32, vp]),
+        "vp_multi_upload_chunks_rle": (C.c_int, [vp, vp, C.c_uint32, vp, vp]),
+        "vp_multi_set_chunks_null": (C.c_int, [vp, vp, C.c_uint32]),
+        "vp_multi_upload_shadow_rows": (C.c_int, [vp, C.c_uint32, C.c_uint32, vp]),
+        "vp_multi_exchange_halos": (C.c_int, [vp, C.c_int32]),
+        "vp_multi_batch_prepare": (C.c_int, [vp, vp, C.c_uint32, vp, C.c_uint32]),
+        "vp_multi_rebuild_device": (C.c_int, [vp, C.c_int32]),
+        "vp_multi_synchronize": (C.c_int, [vp]),
+        "vp_multi_rebuild_batch": (C.c_int, [vp, vp, C.c_uint32, C.c_uint32, vp, vp, vp, vp, vp]),
         "vp_halo_pack": (C.c_int, [vp, C.c_int, vp]),
         "vp_halo_unpack": (C.c_int, [vp, C.c_int, vp]),
     }
@@ -385,8 +402,77 @@ class Context:
     def halo_plane_bytes(self):
         return int(self.lib.vp_halo_plane_bytes(self.h))
 
+    def border_stream_handle(self):
+        """cudaStream_t (as int) on which halo_pack / halo_unpack / rebuild_device_part(1) run."""
+        return int(self.lib.vp_ctx_border_stream(self.h) or 0)
+
     def halo_pack(self, which, device_ptr):
         self._ck(self.lib.vp_halo_pack(self.h, which, C.c_void_p(device_ptr)))
 
     def halo_unpack(self, which, device_ptr):
         self._ck(self.lib.vp_halo_unpack(self.h, which, C.c_void_p(device_ptr)))
+
+
+class MultiContext:
+    """Several GPUs behind one handle, one host thread (struct vp_multi): z-slabs of chunk rows, border planes pushed
+    peer to peer.  `devices` may repeat a device (several slabs on one GPU: used by the tests on 1-GPU boxes)."""
+
+    def __init__(self, root_bitw, max_bitw, devices, splat_arena_bytes=0, mesh_arena_bytes=0, rle_arena_bytes=0):
+        self.lib = load_library()
+        cfg = VpConfig()
+        cfg.root_bitw = root_bitw
+        cfg.max_bitw = (C.c_int32 * 3)(*max_bitw)
+        cfg.splat_arena_bytes, cfg.mesh_arena_bytes, cfg.rle_arena_bytes = splat_arena_bytes, mesh_arena_bytes, rle_arena_bytes
+        devs = (C.c_int32 * len(devices))(*devices)
+        h = C.c_void_p()
+        rc = self.lib.vp_multi_create(C.byref(cfg), devs, len(devices), C.byref(h))
+        if rc:
+            raise VoxplatError(rc, self.lib.vp_multi_last_error(None).decode())
+        self.h, self.n_dev = h, len(devices)
+        self.root_bitw, self.max_bitw = root_bitw, tuple(max_bitw)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.vp_multi_destroy(self.h)
+            self.h = None
+
+    def _ck(self, rc):
+        if rc:
+            raise VoxplatError(rc, self.lib.vp_multi_last_error(self.h).decode())
+
+    def upload_chunks_dense(self, ids, dense):
+        ids = _u32(ids)
+        self._ck(self.lib.vp_multi_upload_chunks_dense(self.h, _ptr(ids), len(ids), _ptr(dense)))
+
+    def upload_chunks_rle(self, ids, words, word_offsets):
+        ids = _u32(ids)
+        words = np.ascontiguousarray(words, dtype=np.uint32)
+        offs = np.ascontiguousarray(word_offsets, dtype=np.uint64)
+        self._ck(self.lib.vp_multi_upload_chunks_rle(self.h, _ptr(ids), len(ids), _ptr(words), _ptr(offs)))
+
+    def set_chunks_null(self, ids):
+        ids = _u32(ids)
+        self._ck(self.lib.vp_multi_set_chunks_null(self.h, _ptr(ids), len(ids)))
+
+    def upload_shadow_rows(self, z0, rows):
+        rows = np.ascontiguousarray(rows, dtype=np.uint16)
+        shw = ((1 << self.max_bitw[0]) + (1 << self.max_bitw[1])) << self.root_bitw
+        self._ck(self.lib.vp_multi_upload_shadow_rows(self.h, z0, z0 + rows.size // shw, _ptr(rows)))
+
+    def rebuild_batch(self, ids, flags=VP_REBUILD_SPLAT, per_chunk_flags=None):
+        """Returns (results, owner, [splat bytes per device], [mesh bytes per device])."""
+        ids = _u32(ids)
+        res = np.zeros(len(ids), RESULT_DTYPE)
+        owner = np.zeros(len(ids), np.uint8)
+        pcf = np.ascontiguousarray(per_chunk_flags, dtype=np.uint8) if per_chunk_flags is not None else None
+        sb, mb = (C.c_void_p * self.n_dev)(), (C.c_void_p * self.n_dev)()
+        self._ck(self.lib.vp_multi_rebuild_batch(self.h, _ptr(ids), len(ids), flags, _ptr(pcf), _ptr(res), _ptr(owner), sb, mb))
+        splat, mesh = [], []
+        for d in range(self.n_dev):
+            m = owner == d
+            s_end = int((res["svl_offset"][m] + res["svl_items_total"][m].astype(np.uint64) * 2).max()) if m.any() else 0
+            m_end = int(np.maximum(res["vbo_offset"][m] + res["vbo_items"][m].astype(np.uint64) * 2,
+                                   res["ibo_offset"][m] + res["ibo_items"][m].astype(np.uint64) * 4).max()) if m.any() else 0
+            splat.append(np.ctypeslib.as_array(C.cast(sb[d], C.POINTER(C.c_uint8)), shape=(s_end,)) if s_end and sb[d] else np.zeros(0, np.uint8))
+            mesh.append(np.ctypeslib.as_array(C.cast(mb[d], C.POINTER(C.c_uint8)), shape=(m_end,)) if m_end and mb[d] else np.zeros(0, np.uint8))
+        return res, owner, splat, mesh

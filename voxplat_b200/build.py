@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.environ.get("VOXPLAT_B200_LIB", os.path.join(HERE, "libvoxplat_b200.so"))
 WORLDGEN = os.path.join(HERE, "libvpworldgen.so")
-CU_SOURCES = ["vp_context.cu", "vp_splat.cu", "vp_mesh.cu", "vp_rle.cu", "vp_nodes.cu", "vp_edit.cu", "vp_worldfile.cu", "vp_worldgen_dev.cu"]
+CU_SOURCES = ["vp_context.cu", "vp_splat.cu", "vp_mesh.cu", "vp_rle.cu", "vp_nodes.cu", "vp_edit.cu", "vp_worldfile.cu", "vp_worldgen_dev.cu", "vp_multi.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--cudart", "static"]
 NVCC_FLAGS += os.environ.get("VP_NVCC_EXTRA", "").split()        # e.g. -DVP_PROFILE_PHASES for an instrumented build

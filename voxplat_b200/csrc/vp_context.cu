@@ -93,13 +93,17 @@ static void ctx_free(vp_ctx *c)
 	cudaFree(c->d_ids); cudaFree(c->d_flags); cudaFree(c->d_splat_ids); cudaFree(c->d_mesh_ids); cudaFree(c->d_results);
 	cudaFree(c->d_splat_pos); cudaFree(c->d_mesh_pos);
 	cudaFree(c->d_splat_arena); cudaFree(c->d_mesh_arena); cudaFree(c->d_rle_arena); cudaFree(c->d_arena_state);
-	cudaFree(c->d_splat_scratch); cudaFree(c->d_mesh_scratch);
+	cudaFree(c->d_splat_scratch); cudaFree(c->d_mesh_scratch); cudaFree(c->d_splat_scratch_b); cudaFree(c->d_mesh_scratch_b);
 	cudaFree(c->d_tmp_slots); cudaFree(c->d_io); cudaFree(c->d_node_arena); cudaFree(c->d_nodes); cudaFreeHost(c->h_node_stage);
 	cudaFreeHost(c->h_results); cudaFreeHost(c->h_arena_state); cudaFreeHost(c->h_splat_stage); cudaFreeHost(c->h_mesh_stage);
 	cudaFreeHost(c->h_io_stage);
 	if (c->own_stream) cudaStreamDestroy(c->own_stream);
 	if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
 	if (c->mesh_stream) cudaStreamDestroy(c->mesh_stream);
+	if (c->border_stream) cudaStreamDestroy(c->border_stream);
+	if (c->ev_reset) cudaEventDestroy(c->ev_reset);
+	if (c->ev_bjoin) cudaEventDestroy(c->ev_bjoin);
+	if (c->ev_bready) cudaEventDestroy(c->ev_bready);
 	if (c->ev_fork) cudaEventDestroy(c->ev_fork);
 	if (c->ev_join) cudaEventDestroy(c->ev_join);
 	if (c->down_stream) cudaStreamDestroy(c->down_stream);
@@ -110,6 +114,8 @@ static void ctx_free(vp_ctx *c)
 	for (int h = 0; h < vp_ctx::kHist; h++) for (int i = 0; i < 4; i++) if (c->ev_k[h][i]) cudaEventDestroy(c->ev_k[h][i]);
 	delete c;
 }
+
+static int ghost_row_init(vp_ctx *c, int row);
 
 extern "C" int vp_ctx_create(const vp_config *cfg, vp_ctx **out)
 {
@@ -153,6 +159,10 @@ extern "C" int vp_ctx_create(const vp_config *cfg, vp_ctx **out)
 		const int prio = (e && e[0] == 'h') ? hi : ((e && e[0] == 'l') ? lo : 0);
 		CK(cudaStreamCreateWithPriority(&c->mesh_stream, cudaStreamNonBlocking, prio));
 	}
+	CK(cudaStreamCreateWithFlags(&c->border_stream, cudaStreamNonBlocking));
+	CK(cudaEventCreateWithFlags(&c->ev_reset, cudaEventDisableTiming));
+	CK(cudaEventCreateWithFlags(&c->ev_bjoin, cudaEventDisableTiming));
+	CK(cudaEventCreateWithFlags(&c->ev_bready, cudaEventDisableTiming));
 	CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
 	CK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
 	CK(cudaStreamCreateWithFlags(&c->down_stream, cudaStreamNonBlocking));
@@ -188,6 +198,14 @@ extern "C" int vp_ctx_create(const vp_config *cfg, vp_ctx **out)
 	memset(c->h_arena_state, 0, 6 * sizeof(VpArenaDev));
 	CK(cudaStreamSynchronize(c->stream));
 #undef CK
+	// Ghost rows (the border slices of the slab neighbours) own permanent zero-filled slots from the start, so that a
+	// border exchange never changes which chunks are resident.
+	for (int side = 0; side < 2; side++) {
+		const int row = side ? c->cfg.slab_z1 : c->cfg.slab_z0 - 1;
+		if (row < c->ez0 || row >= c->ez1 || (row >= c->cfg.slab_z0 && row < c->cfg.slab_z1)) continue;
+		const int rc = ghost_row_init(c, row);
+		if (rc) { g_create_err = c->err; ctx_free(c); return rc; }
+	}
 	*out = c;
 	return VP_OK;
 }
@@ -246,26 +264,39 @@ static inline bool all_zero(const uint8_t *p, size_t n)
 	return acc == 0;
 }
 
-// assign / release slots for a list of chunks; want[i] != 0 means the chunk needs storage
+// assign / release slots for a list of chunks; want[i] != 0 means the chunk needs storage.  All ids and the pool capacity
+// are checked BEFORE any state changes, so a failing call leaves the host and device slot tables as they were.
 static int assign_slots(vp_ctx *c, const uint32_t *ids, uint32_t n, const uint8_t *want, std::vector<int32_t> &slots)
 {
 	slots.resize(n);
+	size_t need = 0, freed = 0;
 	for (uint32_t i = 0; i < n; i++) {
-		int64_t e = ext_index(c, ids[i]);
+		const int64_t e = ext_index(c, ids[i]);
 		if (e < 0) return vp_fail(c, VP_ERR_NOT_RESIDENT, "chunk id outside this context's slab");
-		int32_t s = c->h_slot[(size_t)e];
-		if (want[i]) {
-			if (s < 0) {
-				if (c->free_slots.empty()) return vp_fail(c, VP_ERR_ARENA_FULL, "chunk pool exhausted");
-				s = (int32_t)c->free_slots.back(); c->free_slots.pop_back();
-				c->h_slot[(size_t)e] = s;
-			}
-		} else if (s >= 0) {
-			c->free_slots.push_back((uint32_t)s);
-			c->h_slot[(size_t)e] = -1; s = -1;
-		}
-		slots[i] = s;
+		const int32_t s = c->h_slot[(size_t)e];
+		if (want[i]) need += s < 0; else freed += s >= 0;
 	}
+	// (a list that names a chunk twice may over-count `need`; that only makes the check conservative)
+	if (need > c->free_slots.size() + freed) return vp_fail(c, VP_ERR_ARENA_FULL, "chunk pool exhausted");
+	for (int pass = 0; pass < 2; pass++)               // releases first: their slots may be handed out again in the same call
+		for (uint32_t i = 0; i < n; i++) {
+			if ((want[i] != 0) != (pass == 1)) continue;
+			const int64_t e = ext_index(c, ids[i]);
+			int32_t s = c->h_slot[(size_t)e];
+			if (want[i]) {
+				if (s < 0) {
+					if (c->free_slots.empty()) return vp_fail(c, VP_ERR_ARENA_FULL, "chunk pool exhausted");      // unreachable: checked above
+					s = (int32_t)c->free_slots.back(); c->free_slots.pop_back();
+					c->h_slot[(size_t)e] = s;
+					c->residency_epoch++;
+				}
+			} else if (s >= 0) {
+				c->free_slots.push_back((uint32_t)s);
+				c->h_slot[(size_t)e] = -1; s = -1;
+				c->residency_epoch++;
+			}
+			slots[i] = s;
+		}
 	return VP_OK;
 }
 
@@ -499,6 +530,7 @@ static int scratch_reserve(vp_ctx *c, uint8_t **buf, uint32_t *cap_chunks, uint3
 	if (n <= *cap_chunks) return VP_OK;
 	VP_CUDA(c, cudaStreamSynchronize(c->stream));
 	VP_CUDA(c, cudaStreamSynchronize(c->mesh_stream));
+	VP_CUDA(c, cudaStreamSynchronize(c->border_stream));
 	cudaFree(*buf); *buf = nullptr; *cap_chunks = 0;
 	const uint32_t cap = std::max<uint32_t>(n + n / 8, 64);
 	VP_CUDA(c, cudaMalloc(buf, bytes_for(c->rb, cap)));
@@ -508,6 +540,8 @@ static int scratch_reserve(vp_ctx *c, uint8_t **buf, uint32_t *cap_chunks, uint3
 }
 static int splat_scratch_reserve(vp_ctx *c, uint32_t n) { return scratch_reserve(c, &c->d_splat_scratch, &c->splat_scratch_chunks, n, vp_splat_scratch_bytes); }
 static int mesh_scratch_reserve(vp_ctx *c, uint32_t n) { return scratch_reserve(c, &c->d_mesh_scratch, &c->mesh_scratch_chunks, n, vp_mesh_scratch_bytes); }
+static int splat_scratch_b_reserve(vp_ctx *c, uint32_t n) { return scratch_reserve(c, &c->d_splat_scratch_b, &c->splat_scratch_b_chunks, n, vp_splat_scratch_bytes); }
+static int mesh_scratch_b_reserve(vp_ctx *c, uint32_t n) { return scratch_reserve(c, &c->d_mesh_scratch_b, &c->mesh_scratch_b_chunks, n, vp_mesh_scratch_bytes); }
 
 extern "C" int vp_batch_prepare(vp_ctx *c, const uint32_t *ids, uint32_t n, const uint8_t *per_chunk_flags, uint32_t flags)
 {
@@ -560,8 +594,11 @@ extern "C" int vp_batch_prepare(vp_ctx *c, const uint32_t *ids, uint32_t n, cons
 		c->n_mesh_int = interior_first(mid, mpos, true);
 	}
 	c->batch_n = n; c->n_splat = (uint32_t)sid.size(); c->n_mesh = (uint32_t)mid.size();
-	if ((rc = splat_scratch_reserve(c, c->n_splat))) return rc;
-	if ((rc = mesh_scratch_reserve(c, c->n_mesh))) return rc;
+	c->batch_epoch = c->residency_epoch;
+	if ((rc = splat_scratch_reserve(c, c->n_splat_int))) return rc;
+	if ((rc = mesh_scratch_reserve(c, c->n_mesh_int))) return rc;
+	if (c->n_splat > c->n_splat_int && (rc = splat_scratch_b_reserve(c, c->n_splat - c->n_splat_int))) return rc;
+	if (c->n_mesh > c->n_mesh_int && (rc = mesh_scratch_b_reserve(c, c->n_mesh - c->n_mesh_int))) return rc;
 	if (c->n_splat) {
 		VP_CUDA(c, cudaMemcpyAsync(c->d_splat_ids, sid.data(), sid.size() * 4, cudaMemcpyHostToDevice, c->stream));
 		VP_CUDA(c, cudaMemcpyAsync(c->d_splat_pos, spos.data(), spos.size() * 4, cudaMemcpyHostToDevice, c->stream));
@@ -588,42 +625,69 @@ extern "C" int vp_rebuild_device_part(vp_ctx *c, int part)
 	if (!c || part < 0 || part > 1) return VP_ERR_ARG;
 	VP_CUDA(c, cudaSetDevice(c->cfg.device));
 	VpWorldDev w = vp_world_dev(c);
+	// the prepared lists leave out chunks that had nothing to show when they were made (null chunk with null +x,+y,+z
+	// neighbours): a chunk that changed between null and resident since then needs a new vp_batch_prepare
+	if (c->batch_epoch != c->residency_epoch)
+		return vp_fail(c, VP_ERR_ARG, "vp_rebuild_device: chunk residency changed since vp_batch_prepare -- prepare the batch again");
 	if (part == 0) {
 		VP_CUDA(c, cudaMemcpyAsync(c->d_arena_state, c->h_arena_state + 3, 2 * sizeof(VpArenaDev), cudaMemcpyHostToDevice, c->stream));
 		VP_CUDA(c, cudaMemsetAsync(c->d_results, 0, (size_t)c->batch_n * sizeof(VpResultDev), c->stream));
+		VP_CUDA(c, cudaEventRecord(c->ev_reset, c->stream));
 		c->ev_k_valid[c->rebuilds % vp_ctx::kHist] = 0;
 		c->rebuilds++;
 	}
 	if (!c->rebuilds) return vp_fail(c, VP_ERR_ARG, "vp_rebuild_device_part: part 1 before part 0");
 	cudaEvent_t *ev = c->ev_k[(c->rebuilds - 1) % vp_ctx::kHist];
 	uint8_t &valid = c->ev_k_valid[(c->rebuilds - 1) % vp_ctx::kHist];
-	const uint32_t s0 = part ? c->n_splat_int : 0, s1 = part ? c->n_splat : c->n_splat_int;
-	const uint32_t m0 = part ? c->n_mesh_int : 0, m1 = part ? c->n_mesh : c->n_mesh_int;
 	const bool fork = c->n_splat && c->n_mesh;
 	cudaStream_t ms = fork ? c->mesh_stream : c->stream;
-	if (fork && (part == 0 || m1 > m0)) {
-		VP_CUDA(c, cudaEventRecord(c->ev_fork, c->stream));
-		VP_CUDA(c, cudaStreamWaitEvent(ms, c->ev_fork, 0));
-	}
-	if (c->n_mesh) {
-		if (part == 0) VP_CUDA(c, cudaEventRecord(ev[2], ms));
-		if (m1 > m0) {
-			VP_CUDA(c, vp_launch_mesh(w, c->d_mesh_ids + m0, m1 - m0, c->d_results, c->d_mesh_pos + m0, c->d_mesh_arena, c->d_arena_state + 1,
-			                          c->d_mesh_scratch, c->mesh_scratch_chunks, ms));
-			c->launches += kMeshLaunches;
+	if (part == 0) {
+		// interior: the chunks that do not read a ghost row.  The mesh kernels (few chunks) run beside the splat kernels.
+		if (fork) {
+			VP_CUDA(c, cudaEventRecord(c->ev_fork, c->stream));
+			VP_CUDA(c, cudaStreamWaitEvent(ms, c->ev_fork, 0));
 		}
-		if (part == 1) { VP_CUDA(c, cudaEventRecord(ev[3], ms)); valid |= 2; }
+		if (c->n_mesh) {
+			VP_CUDA(c, cudaEventRecord(ev[2], ms));
+			if (c->n_mesh_int) {
+				VP_CUDA(c, vp_launch_mesh(w, c->d_mesh_ids, c->n_mesh_int, c->d_results, c->d_mesh_pos, c->d_mesh_arena, c->d_arena_state + 1,
+				                          c->d_mesh_scratch, c->mesh_scratch_chunks, ms));
+				c->launches += kMeshLaunches;
+			}
+		}
+		if (c->n_splat) {
+			VP_CUDA(c, cudaEventRecord(ev[0], c->stream));
+			if (c->n_splat_int) {
+				VP_CUDA(c, vp_launch_splat(w, c->d_splat_ids, c->n_splat_int, c->d_results, c->d_splat_pos, c->d_splat_arena, c->d_arena_state + 0,
+				                           c->d_splat_scratch, c->splat_scratch_chunks, c->stream));
+				c->launches += kSplatLaunches;
+			}
+		}
+		return VP_OK;
 	}
-	if (c->n_splat) {
-		if (part == 0) VP_CUDA(c, cudaEventRecord(ev[0], c->stream));
-		if (s1 > s0) {
-			VP_CUDA(c, vp_launch_splat(w, c->d_splat_ids + s0, s1 - s0, c->d_results, c->d_splat_pos + s0, c->d_splat_arena, c->d_arena_state + 0,
-			                           c->d_splat_scratch, c->splat_scratch_chunks, c->stream));
+	// part 1: the slab's border chunks on the border stream -- behind the unpack of the received planes (vp_halo_unpack
+	// runs there too) and BESIDE the interior kernels, with their own scratch; both parts bump the same arena cursors.
+	const uint32_t sb = c->n_splat - c->n_splat_int, mb = c->n_mesh - c->n_mesh_int;
+	if (sb || mb) {
+		cudaStream_t bs = c->border_stream;
+		VP_CUDA(c, cudaStreamWaitEvent(bs, c->ev_reset, 0));            // arena cursors and result records are reset
+		if (sb) {
+			VP_CUDA(c, vp_launch_splat(w, c->d_splat_ids + c->n_splat_int, sb, c->d_results, c->d_splat_pos + c->n_splat_int, c->d_splat_arena,
+			                           c->d_arena_state + 0, c->d_splat_scratch_b, c->splat_scratch_b_chunks, bs));
 			c->launches += kSplatLaunches;
 		}
-		if (part == 1) { VP_CUDA(c, cudaEventRecord(ev[1], c->stream)); valid |= 1; }
+		if (mb) {
+			VP_CUDA(c, vp_launch_mesh(w, c->d_mesh_ids + c->n_mesh_int, mb, c->d_results, c->d_mesh_pos + c->n_mesh_int, c->d_mesh_arena,
+			                          c->d_arena_state + 1, c->d_mesh_scratch_b, c->mesh_scratch_b_chunks, bs));
+			c->launches += kMeshLaunches;
+		}
+		VP_CUDA(c, cudaEventRecord(c->ev_bjoin, bs));
+		VP_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_bjoin, 0));
+		if (fork) VP_CUDA(c, cudaStreamWaitEvent(ms, c->ev_bjoin, 0));
 	}
-	if (fork && part == 1) {
+	if (c->n_mesh) { VP_CUDA(c, cudaEventRecord(ev[3], ms)); valid |= 2; }
+	if (c->n_splat) { VP_CUDA(c, cudaEventRecord(ev[1], c->stream)); valid |= 1; }
+	if (fork) {
 		VP_CUDA(c, cudaEventRecord(c->ev_join, ms));
 		VP_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_join, 0));
 	}
@@ -699,6 +763,21 @@ extern "C" int vp_ctx_resize_arenas(vp_ctx *c, uint64_t splat_bytes, uint64_t me
 	return VP_OK;
 }
 
+// The first sb / mb bytes of the splat / mesh arenas into the context's pinned staging (grown on demand).
+int vp_stage_arenas(vp_ctx *c, uint64_t sb, uint64_t mb, const void **splat_base, const void **mesh_base)
+{
+	int rc;
+	VP_CUDA(c, cudaSetDevice(c->cfg.device));
+	if ((rc = stage_reserve(c, &c->h_splat_stage, &c->splat_stage_cap, sb))) return rc;
+	if ((rc = stage_reserve(c, &c->h_mesh_stage, &c->mesh_stage_cap, mb))) return rc;
+	if (sb) VP_CUDA(c, cudaMemcpyAsync(c->h_splat_stage, c->d_splat_arena, sb, cudaMemcpyDeviceToHost, c->stream));
+	if (mb) VP_CUDA(c, cudaMemcpyAsync(c->h_mesh_stage, c->d_mesh_arena, mb, cudaMemcpyDeviceToHost, c->stream));
+	VP_CUDA(c, cudaStreamSynchronize(c->stream));
+	if (splat_base) *splat_base = c->h_splat_stage;
+	if (mesh_base) *mesh_base = c->h_mesh_stage;
+	return VP_OK;
+}
+
 extern "C" int vp_rebuild_batch(vp_ctx *c, const uint32_t *ids, uint32_t n, uint32_t flags, const uint8_t *per_chunk_flags,
                                 vp_chunk_result *results, const void **splat_base, const void **mesh_base)
 {
@@ -709,14 +788,7 @@ extern "C" int vp_rebuild_batch(vp_ctx *c, const uint32_t *ids, uint32_t n, uint
 	uint64_t sb = 0, mb = 0;
 	rc = vp_rebuild_device_results(c, results, &sb, &mb);
 	if (rc) return rc;
-	if ((rc = stage_reserve(c, &c->h_splat_stage, &c->splat_stage_cap, sb))) return rc;
-	if ((rc = stage_reserve(c, &c->h_mesh_stage, &c->mesh_stage_cap, mb))) return rc;
-	if (sb) VP_CUDA(c, cudaMemcpyAsync(c->h_splat_stage, c->d_splat_arena, sb, cudaMemcpyDeviceToHost, c->stream));
-	if (mb) VP_CUDA(c, cudaMemcpyAsync(c->h_mesh_stage, c->d_mesh_arena, mb, cudaMemcpyDeviceToHost, c->stream));
-	VP_CUDA(c, cudaStreamSynchronize(c->stream));
-	if (splat_base) *splat_base = c->h_splat_stage;
-	if (mesh_base) *mesh_base = c->h_mesh_stage;
-	return VP_OK;
+	return vp_stage_arenas(c, sb, mb, splat_base, mesh_base);
 }
 
 // ---- single-chunk wrappers (mesher.h:7-37 semantics) ------------------------------------------------
@@ -779,7 +851,10 @@ extern "C" int vp_halo_pack(vp_ctx *c, int which, void *device_buf)
 	const uint32_t per_row = (uint32_t)c->nx * c->ny;
 	const int row = which == 0 ? c->cfg.slab_z0 : c->cfg.slab_z1 - 1;
 	const int32_t *row_slots = c->d_slot + (size_t)(row - c->ez0) * per_row;
-	k_plane_copy<<<per_row, 256, 0, c->stream>>>(c->rb, c->vox_pool, row_slots, (uint8_t *)device_buf, which == 0 ? 0 : c->R - 1, 0);
+	// on the border stream, behind whatever the context stream has done to the voxels so far
+	VP_CUDA(c, cudaEventRecord(c->ev_bready, c->stream));
+	VP_CUDA(c, cudaStreamWaitEvent(c->border_stream, c->ev_bready, 0));
+	k_plane_copy<<<per_row, 256, 0, c->border_stream>>>(c->rb, c->vox_pool, row_slots, (uint8_t *)device_buf, which == 0 ? 0 : c->R - 1, 0);
 	VP_CUDA(c, cudaGetLastError());
 	c->launches++;
 	return VP_OK;
@@ -797,12 +872,17 @@ extern "C" int vp_halo_unpack(vp_ctx *c, int which, const void *device_buf)
 	int rc = ghost_row_init(c, row);
 	if (rc) return rc;
 	const int32_t *row_slots = c->d_slot + (size_t)(row - c->ez0) * per_row;
-	k_plane_copy<<<per_row, 256, 0, c->stream>>>(c->rb, c->vox_pool, row_slots, (uint8_t *)const_cast<void *>(device_buf), which == 0 ? 0 : c->R - 1, 1);
+	k_plane_copy<<<per_row, 256, 0, c->border_stream>>>(c->rb, c->vox_pool, row_slots, (uint8_t *)const_cast<void *>(device_buf), which == 0 ? 0 : c->R - 1, 1);
 	VP_CUDA(c, cudaGetLastError());
-	VP_CUDA(c, vp_launch_extract_xfaces(c->rb, c->vox_pool, c->xlo_pool, c->xhi_pool, row_slots, per_row, c->stream));
+	VP_CUDA(c, vp_launch_extract_xfaces(c->rb, c->vox_pool, c->xlo_pool, c->xhi_pool, row_slots, per_row, c->border_stream));
 	c->launches += 2;
+	// anything the caller enqueues on the context stream next (e.g. vp_rebuild_batch of border chunks) sees the planes
+	VP_CUDA(c, cudaEventRecord(c->ev_bjoin, c->border_stream));
+	VP_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_bjoin, 0));
 	return VP_OK;
 }
+
+extern "C" void *vp_ctx_border_stream(vp_ctx *c) { return c ? (void *)c->border_stream : nullptr; }
 
 // ------------------------------------------------------------------------------------------------
 // RLE: upload + decode, encode of resident chunks, flat codec

@@ -64,6 +64,8 @@ struct vp_ctx {
 	cudaStream_t own_stream, stream;
 	cudaStream_t copy_stream, down_stream;
 	cudaStream_t mesh_stream;     // the mesh kernel of a rebuild runs beside the splat kernels
+	cudaStream_t border_stream;   // slab contexts: border pack / unpack and the rebuild of the chunks that read a ghost row
+	cudaEvent_t ev_reset, ev_bjoin, ev_bready;
 	cudaEvent_t ev_fork, ev_join;
 	cudaEvent_t ev_pipe[2][64];   // [0] decode done, [1] kernels done, per pipeline step
 	VpArenaDev *h_steps;          // pinned: arena states after every pipeline step [64][2], then 64 uint32 step tickets
@@ -83,6 +85,7 @@ struct vp_ctx {
 	uint16_t *d_shadow; uint32_t sh_z0, sh_z1; size_t shadow_entries;
 	// batch state
 	uint32_t *d_ids; uint8_t *d_flags; uint32_t batch_n, batch_cap; uint32_t batch_flags;
+	uint64_t residency_epoch, batch_epoch;               // bumped by every null <-> resident change / value at the last vp_batch_prepare
 	uint32_t *d_splat_ids, *d_mesh_ids; uint32_t n_splat, n_mesh;
 	uint32_t n_splat_int, n_mesh_int;                    // list entries that do not read a ghost row come first
 	uint32_t *d_splat_pos, *d_mesh_pos;                  // position in the batch of each list entry
@@ -98,12 +101,15 @@ struct vp_ctx {
 	uint8_t *h_node_stage; size_t node_stage_cap;
 	uint8_t *d_splat_scratch; uint32_t splat_scratch_chunks;  // arrival counters + slab records of the splat kernel
 	uint8_t *d_mesh_scratch; uint32_t mesh_scratch_chunks;    // occupancy tiles / counts between the mesh kernels
+	uint8_t *d_splat_scratch_b; uint32_t splat_scratch_b_chunks;   // the same for the border part of a slab step (runs beside the interior part)
+	uint8_t *d_mesh_scratch_b; uint32_t mesh_scratch_b_chunks;
 	uint8_t *d_io; size_t d_io_cap;                      // device scratch for the flat RLE codec / stream offsets
 	uint64_t launches;
 	std::string err;
 };
 
 VpWorldDev vp_world_dev(const vp_ctx *c);
+int vp_stage_arenas(vp_ctx *c, uint64_t sb, uint64_t mb, const void **splat_base, const void **mesh_base);
 int vp_fail(vp_ctx *c, int code, const char *what, cudaError_t e = cudaSuccess);
 #define VP_CUDA(ctx, call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return vp_fail(ctx, VP_ERR_CUDA, #call, e__); } while (0)
 

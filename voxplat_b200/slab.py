@@ -8,6 +8,8 @@ travel with NCCL point-to-point (torch.distributed, NVLink) between slab neighbo
 is on the data path.  PyTorch is plumbing here (device buffers for NCCL, streams); pack / unpack and all
 compute are kernels of the C-ABI library.
 """
+import contextlib
+
 import numpy as np
 
 
@@ -47,6 +49,19 @@ class SlabRebuilder:
         # one buffer per (direction, which); allocated once, reused every exchange
         self.buf = {("send", 0): make_buffer(n), ("recv", 0): make_buffer(n),
                     ("send", 1): make_buffer(n), ("recv", 1): make_buffer(n)}
+        # The CUDA store packs / unpacks on its own border stream; the transport must be ordered against that stream,
+        # which is what torch.distributed does with the CURRENT stream of the calling thread.
+        self._border = None
+        handle = store.border_stream_handle() if hasattr(store, "border_stream_handle") else 0
+        if handle:
+            import torch
+            self._border = torch.cuda.ExternalStream(handle)
+
+    def _on_border_stream(self):
+        if self._border is None:
+            return contextlib.nullcontext()
+        import torch
+        return torch.cuda.stream(self._border)
 
     def exchange_begin(self, mesh=False):
         """Pack my border planes and start the swap with the slab neighbours; returns the pending requests.
@@ -55,14 +70,15 @@ class SlabRebuilder:
         if self.world_size == 1:
             return None
         plan = halo_schedule(self.rank, self.world_size, mesh)
-        for op, which, _ in plan:
-            if op == "send":
-                self.store.halo_pack(which, self.buf[(op, which)].data_ptr())
-        ops = []
-        for op, which, peer in plan:
-            fn = self.dist.isend if op == "send" else self.dist.irecv
-            ops.append(self.dist.P2POp(fn, self.buf[(op, which)], peer, group=self.group))
-        reqs = self.dist.batch_isend_irecv(ops) if ops else []
+        with self._on_border_stream():
+            for op, which, _ in plan:
+                if op == "send":
+                    self.store.halo_pack(which, self.buf[(op, which)].data_ptr())
+            ops = []
+            for op, which, peer in plan:
+                fn = self.dist.isend if op == "send" else self.dist.irecv
+                ops.append(self.dist.P2POp(fn, self.buf[(op, which)], peer, group=self.group))
+            reqs = self.dist.batch_isend_irecv(ops) if ops else []
         return plan, reqs
 
     def exchange_finish(self, pending):
@@ -70,11 +86,12 @@ class SlabRebuilder:
         if pending is None:
             return 0
         plan, reqs = pending
-        for req in reqs:
-            req.wait()
-        for op, which, _ in plan:
-            if op == "recv":
-                self.store.halo_unpack(which, self.buf[(op, which)].data_ptr())
+        with self._on_border_stream():
+            for req in reqs:
+                req.wait()
+            for op, which, _ in plan:
+                if op == "recv":
+                    self.store.halo_unpack(which, self.buf[(op, which)].data_ptr())
         return len(plan)
 
     def exchange_halos(self, mesh=False):
@@ -82,8 +99,9 @@ class SlabRebuilder:
         return self.exchange_finish(self.exchange_begin(mesh))
 
     def rebuild_step(self, mesh=True):
-        """One device-resident rebuild of the prepared batch with the border exchange hidden behind the chunks that do
-        not need it (store = a voxplat_b200.Context)."""
+        """One device-resident rebuild of the prepared batch with the border work -- pack, NCCL transfer, unpack and the
+        rebuild of the chunks that read a ghost row (part 1) -- on the store's border stream, beside the chunks that do
+        not need it (part 0, context stream).  store = a voxplat_b200.Context."""
         pending = self.exchange_begin(mesh)
         self.store.rebuild_device_part(0)
         self.exchange_finish(pending)
