@@ -269,7 +269,8 @@ VR_EXPORT uint64_t vr_fnv1a(const void *p, uint64_t n) { return fnv1a(p, (size_t
  * the throttle-free best case of chunkset_manage's loop.
  *   mode 0 = splat path, mode 1 = mesh path.
  * Outputs per chunk: hash (FNV-1a 64 of the output bytes; for mesh VBO then IBO), counts[8]
- * (splat: items[0..4]; mesh: [5]=vbo items, [6]=ibo items).  Returns seconds of wall time.
+ * (splat: items[0..4]; mesh: [5]=vbo items, [6]=ibo items).  Returns seconds of wall time.  With hashes == NULL
+ * nothing is hashed (timing runs: only the reference's own work is inside the clock).
  */
 VR_EXPORT double vr_world_rebuild(struct ChunkSet *set, const uint32_t *ids, uint32_t n_ids, int mode,
                                   int nthreads, uint64_t *hashes, uint32_t *counts)
@@ -282,14 +283,16 @@ VR_EXPORT double vr_world_rebuild(struct ChunkSet *set, const uint32_t *ids, uin
 		uint32_t id = ids ? ids[k] : k;
 		struct vr_scratch *s = scratch_get(set);
 		uint32_t it[8] = {0};
-		uint64_t h;
+		uint64_t h = 0;                    /* hashes == NULL: a timing run, the outputs are not read back */
 		if (mode == 0) {
 			int n = vr_chunk_splat(set, id, NULL, 0, it);
-			h = fnv1a(s->geom, (size_t)n * 2, 1469598103934665603ull);
+			if (hashes) h = fnv1a(s->geom, (size_t)n * 2, 1469598103934665603ull);
 		} else {
 			vr_chunk_mesh(set, id, NULL, 0, NULL, 0, &it[5], &it[6]);
-			h = fnv1a(s->geom, (size_t)it[5] * 2, 1469598103934665603ull);
-			h = fnv1a(s->work, (size_t)it[6] * 4, h);
+			if (hashes) {
+				h = fnv1a(s->geom, (size_t)it[5] * 2, 1469598103934665603ull);
+				h = fnv1a(s->work, (size_t)it[6] * 4, h);
+			}
 		}
 		if (hashes) hashes[k] = h;
 		if (counts) memcpy(counts + (size_t)k * 8, it, sizeof(it));

@@ -302,14 +302,16 @@ VO_EXPORT double vo_world_rebuild(const vo_world *w, const uint32_t *ids, uint32
 		#pragma omp for schedule(dynamic, 1)
 		for (uint32_t k = 0; k < n_ids; k++) {
 			uint32_t id = ids ? ids[k] : k, it[8] = {0};
-			uint64_t h;
+			uint64_t h = 0;                /* hashes == NULL: a timing run, nothing is hashed */
 			if (mode == 0) {
 				uint32_t n = vo_chunk_splat(w, id, geom, it);
-				h = vo_fnv1a(geom, (uint64_t)n * 2, 0);
+				if (hashes) h = vo_fnv1a(geom, (uint64_t)n * 2, 0);
 			} else {
 				vo_chunk_mesh(w, id, geom, idx, &it[5], &it[6]);
-				h = vo_fnv1a(geom, (uint64_t)it[5] * 2, 0);
-				h = vo_fnv1a(idx, (uint64_t)it[6] * 4, h);
+				if (hashes) {
+					h = vo_fnv1a(geom, (uint64_t)it[5] * 2, 0);
+					h = vo_fnv1a(idx, (uint64_t)it[6] * 4, h);
+				}
 			}
 			if (hashes) hashes[k] = h;
 			if (counts) memcpy(counts + (size_t)k * 8, it, sizeof it);

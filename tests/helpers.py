@@ -83,12 +83,13 @@ class OracleWorld:
         assert nv.value == f * 16 and ni.value == f * 6
         return vbo[:nv.value].copy(), ibo[:ni.value].copy()
 
-    def rebuild(self, ids, mode, nthreads=0):
+    def rebuild(self, ids, mode, nthreads=0, hashed=True):
+        """hashed=False: a timing run (no FNV pass over the outputs inside the clock); the hashes come back zero."""
         ids = np.ascontiguousarray(ids, dtype=np.uint32)
         hashes = np.zeros(len(ids), np.uint64)
         counts = np.zeros((len(ids), 8), np.uint32)
         t = self.lib.vo_world_rebuild(C.byref(self.w), vp(ids), C.c_uint32(len(ids)), C.c_int(mode), C.c_int(nthreads),
-                                      vp(hashes), vp(counts))
+                                      vp(hashes) if hashed else None, vp(counts))
         return t, hashes, counts
 
 
@@ -119,10 +120,16 @@ class RefWorld:
         assert self.lib is not None
         self.world = world
         self.set = C.c_void_p(self.lib.vr_world_create(world.root_bitw, *world.max_bitw))
-        for i in range(world.n_chunks):
-            if world.solid[i]:
-                self.lib.vr_world_set_chunk(self.set, C.c_uint32(i), C.c_void_p(world.dense[i].ctypes.data))
-        self.lib.vr_world_set_shadow(self.set, vp(world.shadow), C.c_uint32(world.shadow.size))
+        for i in np.nonzero(world.solid)[0]:
+            self.lib.vr_world_set_chunk(self.set, C.c_uint32(int(i)), C.c_void_p(world.dense[int(i)].ctypes.data))
+        if hasattr(world, "shadow_pieces"):
+            # a sparse world: only the rows it holds are written into the reference's (zero-filled, padded) map
+            self.lib.vr_shadow_ptr.restype = C.c_void_p
+            base = self.lib.vr_shadow_ptr(self.set)
+            for z0, rows in world.shadow_pieces:
+                C.memmove(base + z0 * world.shw * 2, rows.ctypes.data, rows.nbytes)
+        else:
+            self.lib.vr_world_set_shadow(self.set, vp(world.shadow), C.c_uint32(world.shadow.size))
         self.R, self.N = world.R, world.N
 
     def splat(self, cid):
@@ -139,13 +146,85 @@ class RefWorld:
                                C.byref(nv), C.byref(ni))
         return vbo[:nv.value].copy(), ibo[:ni.value].copy()
 
-    def rebuild(self, ids, mode, nthreads=0):
+    def rebuild(self, ids, mode, nthreads=0, hashed=True):
+        """hashed=False: a timing run (no FNV pass over the outputs inside the clock); the hashes come back zero."""
         ids = np.ascontiguousarray(ids, dtype=np.uint32)
         hashes = np.zeros(len(ids), np.uint64)
         counts = np.zeros((len(ids), 8), np.uint32)
         t = self.lib.vr_world_rebuild(self.set, vp(ids), C.c_uint32(len(ids)), C.c_int(mode), C.c_int(nthreads),
-                                      vp(hashes), vp(counts))
+                                      vp(hashes) if hashed else None, vp(counts))
         return t, hashes, counts
+
+    def edit_sphere(self, x, y, z, r, v):
+        """chunkset_edit_sphere (edit.c:179-244) on the reference's own ChunkSet."""
+        self.lib.vr_edit_sphere(self.set, x, y, z, r, v)
+
+
+class SparseWorld:
+    """Some chunk rows (z rows of chunks) of a synthetic world held on the host; every other chunk is absent, i.e. air for
+    whoever reads it.  This is what a parity check of a few chunk rows of a very large world needs (bench.py's parity
+    guard): a chunk of row r has the reference's splat buffer when rows r and r+1 are held, and the reference's mesh
+    buffer when rows r-1, r, r+1 are (rows outside the world count as held).  repeat_bits: the world is that smaller
+    world repeated along z (bench.py's weak scaling)."""
+
+    def __init__(self, seed, root_bitw, max_bitw, rows, repeat_bits=None):
+        from voxplat_b200 import worldgen
+        self.seed, self.root_bitw, self.max_bitw = seed, root_bitw, tuple(max_bitw)
+        self.R = 1 << root_bitw
+        self.N = self.R ** 3
+        self.n_chunks = 1 << sum(max_bitw)
+        self.dims = tuple((1 << b) * self.R for b in max_bitw)
+        self.shw = self.dims[0] + self.dims[1]
+        nz = 1 << max_bitw[2]
+        per_row = 1 << (max_bitw[0] + max_bitw[1])
+        self.rows = sorted(set(int(r) for r in rows if 0 <= r < nz))
+        self.ids = np.concatenate([np.arange(r * per_row, (r + 1) * per_row, dtype=np.uint32) for r in self.rows])
+        if repeat_bits is not None and tuple(repeat_bits) != tuple(max_bitw):
+            base_rows = 1 << repeat_bits[2]
+            gen_ids = (((self.ids // per_row) % base_rows) * per_row + self.ids % per_row).astype(np.uint32)
+            self._dense, solid = worldgen.gen_chunks(seed, root_bitw, repeat_bits, gen_ids)
+        else:
+            self._dense, solid = worldgen.gen_chunks(seed, root_bitw, max_bitw, self.ids)
+        self.solid = np.zeros(self.n_chunks, np.uint32)
+        self.solid[self.ids] = solid
+        self._pos = np.full(self.n_chunks, -1, np.int64)
+        self._pos[self.ids] = np.arange(len(self.ids))
+        ptrs = self.chunk_ptrs()
+        # the height map: rows of the held chunk rows only (a voxel row z depends on the chunks of chunk row z / R alone)
+        self.shadow = np.zeros(self.shw * self.dims[2] + worldgen.shadow_pad(root_bitw, max_bitw), np.uint16)   # untouched pages cost nothing
+        self.shadow_pieces = []
+        for r in self.rows:
+            rows_r = worldgen.shadow_rows(seed, root_bitw, max_bitw, ptrs, r * self.R, (r + 1) * self.R)
+            self.shadow[r * self.R * self.shw:(r + 1) * self.R * self.shw] = rows_r
+            self.shadow_pieces.append((r * self.R, rows_r))
+
+    class _Dense:
+        def __init__(self, w):
+            self.w = w
+
+        def __getitem__(self, i):
+            k = self.w._pos[i]
+            assert k >= 0, "chunk %d is not held by this sparse world" % i
+            return self.w._dense[k]
+
+    @property
+    def dense(self):
+        return SparseWorld._Dense(self)
+
+    def chunk_ptrs(self):
+        base = self._dense.ctypes.data
+        ptrs = [0] * self.n_chunks
+        for k, cid in enumerate(self.ids):
+            if self.solid[cid]:
+                ptrs[int(cid)] = base + k * self.N
+        return ptrs
+
+    def checkable(self, mesh):
+        """Chunk rows whose reference buffers this world can produce."""
+        nz = 1 << self.max_bitw[2]
+        have = set(self.rows)
+        ok = lambda r: r < 0 or r >= nz or r in have
+        return [r for r in self.rows if ok(r + 1) and (not mesh or ok(r - 1))]
 
 
 def random_world(seed, root_bitw, max_bitw, density=0.3, null_frac=0.2, maxv=255, shadow_random=True):
