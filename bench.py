@@ -36,6 +36,7 @@ ROOT_BITW = 6
 BASE_BITS = (5, 2, 5)          # 2048 x 256 x 2048 voxels in 64^3 chunks
 METRIC = "Gvoxel/s culled+meshed (full-world chunk rebuild)"
 DATA = "synthetic (seeded integer worldgen, seed 1234)"
+E2E_BLOCKS = int(os.environ.get("VP_BENCH_E2E_BLOCKS", "8"))     # pipeline depth of the end-to-end call
 
 WORKLOADS = {            # chunk-grid bit widths (64^3 chunks); c2 grows along z with the GPU count (weak scaling)
     "c2": None,           # BASELINE config 2: 2048 x 256 x 2048 per GPU
@@ -491,6 +492,14 @@ def run_world(args, comm, workload, steps, warmup, with_cpu=False, with_mesh_all
             ctx.rebuild_device()
         comm.barrier()
         splat_iso_ms, _ = ctx.kernel_ms_history(iso_n)
+        # ... and the mesh kernels of the near-field chunks alone
+        mesh_iso_ms = [0.0]
+        if near.any():
+            ctx.batch_prepare(own_ids[near], flags=vpb.VP_REBUILD_MESH)
+            for _ in range(iso_n):
+                ctx.rebuild_device()
+            comm.barrier()
+            _, mesh_iso_ms = ctx.kernel_ms_history(iso_n)
         mesh_all = None
         if with_mesh_all:
             # stress figure of SURVEY 8(d): the quad mesh of EVERY chunk (the game meshes only the near field)
@@ -532,7 +541,7 @@ def run_world(args, comm, workload, steps, warmup, with_cpu=False, with_mesh_all
                 if len(border[0]):
                     ctx.upload_chunks_rle(*border)                  # rle_decompress of the border rows on the device
                 rebuilder.exchange_halos(mesh=True)
-            return ctx.rebuild_from_rle(nn_ids, pinned_words, offs, per_chunk_flags=nn_flags, n_blocks=8)
+            return ctx.rebuild_from_rle(nn_ids, pinned_words, offs, per_chunk_flags=nn_flags, n_blocks=E2E_BLOCKS)
 
         for _ in range(3):
             r_e, sb_e, mb_e = e2e_step()
@@ -603,12 +612,12 @@ def run_world(args, comm, workload, steps, warmup, with_cpu=False, with_mesh_all
                          "kernel_ms_alone": k_iso, "frac_alone": sb_a / (k_iso * 1e-3) / 1e9 / peak,
                          "step": {"algorithmic_bytes": sb_a + mb_a, "achieved": (sb_a + mb_a) / (ms_per_step * 1e-3) / 1e9,
                                   "frac": (sb_a + mb_a) / (ms_per_step * 1e-3) / 1e9 / peak},
-                         "mesh_kernel": {"kernel_ms": float(np.mean(mesh_ms)), "algorithmic_bytes_per_launch": mb_a,
+                         "mesh_kernel": {"kernel_ms": float(np.mean(mesh_ms)), "kernel_ms_alone": float(np.mean(mesh_iso_ms)), "algorithmic_bytes_per_launch": mb_a,
                                          "achieved": mb_a / max(float(np.mean(mesh_ms)), 1e-9) / 1e6}},
             "e2e": {"value": e2e_value, "unit": "Gvoxel/s", "h2d_bytes_per_step": int(agg[4]), "d2h_bytes_per_step": int(agg[5]),
                     "ms_per_step": e2e_ms, "steps": e2e_steps, "pcie_floor_ms": floor_ms,
                     "pcie_floor_note": "the same H2D + D2H bytes per rank as plain pinned copies on two streams, all ranks at once, max over ranks",
-                    "path": ("host RLE streams (pinned) -> vp_rebuild_from_rle (8 blocks pipelined: H2D + device decode | cull/LOD/splat/mesh | D2H) -> pinned host staging"
+                    "path": ("host RLE streams (pinned) -> vp_rebuild_from_rle (%d blocks pipelined: H2D + device decode | cull/LOD/splat/mesh | D2H) -> pinned host staging" % E2E_BLOCKS
                              if world_size == 1 else "host RLE streams (pinned) -> border rows: vp_upload_chunks_rle + NCCL plane exchange -> vp_rebuild_from_rle (8 blocks pipelined) -> pinned host staging"),
                     "gpu_launches_per_step": int(e2e_launches)},
             "parity": {"chunks": int(agg[7]), "border_chunks": int(agg[8]), "ok": agg[9] == 0, "checker": chk_kind,

@@ -1,5 +1,11 @@
 mkdir -p gpurun_out
-nvidia-smi topo -m > gpurun_out/r2q_topo.txt 2>&1
-timeout 600 python -m pytest tests/test_gpu_multi.py tests/test_gpu_multictx.py tests/test_gpu_dropin.py -q -x > gpurun_out/r2q_tests.log 2>&1; echo "tests rc=$?" >> gpurun_out/r2q_tests.log; tail -3 gpurun_out/r2q_tests.log
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/multi_gpu_check.py > gpurun_out/r2q_multi_gpu_check.log 2>&1; tail -2 gpurun_out/r2q_multi_gpu_check.log
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 20 --warmup 5 > gpurun_out/r2q_bench2.json 2> gpurun_out/r2q_bench2.err; echo "bench rc=$?"; tail -c 400 gpurun_out/r2q_bench2.err
+timeout 900 python -m pytest tests -m gpu -q -x > gpurun_out/r2s_tests.log 2>&1; echo "tests rc=$?" >> gpurun_out/r2s_tests.log; tail -3 gpurun_out/r2s_tests.log
+for b in 8 16 32; do
+  VP_BENCH_E2E_BLOCKS=$b timeout 300 python bench.py --steps 20 --warmup 5 --no-extra --no-cpu-baseline > gpurun_out/r2s_bench_$b.json 2>/dev/null; echo "blocks $b rc=$?"
+done
+python - <<'PY'
+import json
+for p in (8,16,32):
+    l=json.loads(open('gpurun_out/r2s_bench_%s.json'%p).read().strip().splitlines()[-1])
+    print(p, "step %.4f"%l["ms_per_step"], "e2e %.3f floor %.3f"%(l["e2e"]["ms_per_step"], l["e2e"]["pcie_floor_ms"]), l["parity"]["ok"], l["e2e"]["gpu_launches_per_step"])
+PY
