@@ -140,7 +140,8 @@ VP_API int  vp_upload_shadow_rows_async(vp_ctx *ctx, uint32_t z0, uint32_t z1, c
 
 /* ---- flat RLE codec: drop-in bodies for rle_compress / rle_decompress (rle.h:7-8) ------------- */
 
-/* Encode `length` bytes; writes at most cap_words words (incl. terminator); *n_words = words needed. */
+/* Encode `length` bytes (any length >= 1, like rle.h:7; a run stops at 0xFFFFFF like rle.c:62); writes at most
+ * cap_words words (incl. terminator); *n_words = words needed. */
 VP_API int  vp_rle_compress(vp_ctx *ctx, const uint8_t *data, uint32_t length,
                      uint32_t *out_words, uint32_t cap_words, uint32_t *n_words);
 /* Decode a 0-terminated stream of n_words words (incl. terminator); *n_bytes = bytes produced. */
@@ -210,6 +211,12 @@ VP_API int  vp_chunk_make_mesh(vp_ctx *ctx, uint32_t chunk_id, int16_t *geometry
  * rebuilds them with vp_rebuild_batch.  No voxel data crosses PCIe. */
 VP_API int  vp_edit_sphere(vp_ctx *ctx, int32_t x, int32_t y, int32_t z, uint32_t radius, uint8_t voxel,
                     uint32_t *dirty_ids, uint32_t cap, uint32_t *n_dirty);
+/* chunkset_edit_raycast_until_solid (chunkset/edit.c:248-314; the pick ray of game.c:212) for n rays at once on the
+ * device copy: origins / vectors are n x 3 floats; coords (n x 3) receives the cell where each walk ended, voxels (n) the
+ * voxel hit (0 = nothing within 4095 steps), normals (n x 3, in/out) gets +1 / -1 on the axis of the last step of a
+ * hit and is left alone otherwise, exactly like the reference's output arguments. */
+VP_API int  vp_raycast(vp_ctx *ctx, uint32_t n, const float *origins, const float *vectors, uint32_t *coords, int8_t *normals,
+                uint8_t *voxels);
 /* Read height-map rows [z0,z1) back (the device copy is authoritative after vp_edit_sphere). */
 VP_API int  vp_download_shadow_rows(vp_ctx *ctx, uint32_t z0, uint32_t z1, uint16_t *rows);
 

@@ -42,8 +42,23 @@ VR_EXPORT int vr_init(uint64_t heap_bytes)
 
 VR_EXPORT uint32_t vr_shadow_pad(struct ChunkSet *set) { return 17 * set->shadow_map_size[0] + 64; }
 
+/* chunkset_manage keeps per-thread scratch in a global that it sizes ONCE, for the first ChunkSet it sees
+ * (chunkset.c:233-271): a process that creates worlds of several chunk sizes (the test suite) has to drop it in between,
+ * or the second world overflows the first one's buffers.  Same layout as the anonymous struct at chunkset.c:233-242. */
+extern struct { void *geom[2]; void *mask[2]; void *work[2]; uint32_t work_size, geom_size, mask_size; uint8_t lock[2]; } mesher[4];
+static void vr_reset_dispatcher_scratch(void)
+{
+	for (int t = 0; t < 4; t++)
+		for (int b = 0; b < 2; b++) {
+			if (mesher[t].geom[b]) { mem_free(mesher[t].geom[b]); mem_free(mesher[t].work[b]); mem_free(mesher[t].mask[b]); }
+			mesher[t].geom[b] = mesher[t].work[b] = mesher[t].mask[b] = NULL;
+			mesher[t].lock[b] = 0;
+		}
+}
+
 VR_EXPORT struct ChunkSet *vr_world_create(int root_bitw, int bx, int by, int bz)
 {
+	vr_reset_dispatcher_scratch();
 	uint8_t mb[3] = { (uint8_t)bx, (uint8_t)by, (uint8_t)bz };
 	struct ChunkSet *set = chunkset_create((uint8_t)root_bitw, mb);   /* game.c:263 */
 	chunkset_clear(set);                                              /* game.c:265 */
@@ -142,6 +157,29 @@ VR_EXPORT void vr_edit_sphere(struct ChunkSet *set, int32_t x, int32_t y, int32_
 {
 	int32_t ws[3] = { x, y, z };
 	chunkset_edit_sphere(set, ws, radius, (Voxel)v);
+}
+
+/* ---- the consumer right after the path: gfx_update_svl (gfx/vsplat.c:197-338), run unmodified against the GL capture
+ * shim (gfx_shim/gl_capture.c).  For a chunk whose splat list was published it rebuilds, for every LOD level, the node
+ * buffer that chunk belongs to. ---- */
+void gfx_update_svl(struct ChunkSet *set, uint32_t index);
+const void *vr_gl_buffer(unsigned int id, size_t *size);
+VR_EXPORT void vr_gfx_update_svl(struct ChunkSet *set, uint32_t id) { gfx_update_svl(set, id); }
+VR_EXPORT int vr_chunk_svl_dirty(struct ChunkSet *set, uint32_t id) { return set->chunks[id].svl_dirty; }
+/* The node buffer of (lod, node index) as the reference left it in "GPU memory": returns GeometrySVL.vbo_items. */
+VR_EXPORT uint32_t vr_gsvl_node(struct ChunkSet *set, int lod, uint32_t node, const void **data, uint64_t *bytes)
+{
+	struct GeometrySVL *g = &set->gsvl[lod][node];
+	size_t size = 0;
+	*data = vr_gl_buffer(g->vbo, &size);
+	*bytes = size;
+	return g->vbo ? g->vbo_items : 0;
+}
+
+/* The pick ray of game.c:212, as is. */
+VR_EXPORT int vr_raycast(struct ChunkSet *set, float *origin, float *vector, uint32_t *coord, int8_t *normal)
+{
+	return (int)chunkset_edit_raycast_until_solid(set, origin, vector, coord, normal);
 }
 
 VR_EXPORT int vr_chunk_dirty(struct ChunkSet *set, uint32_t id, int clear)

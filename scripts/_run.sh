@@ -1,11 +1,6 @@
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -q -x > gpurun_out/r2s_tests.log 2>&1; echo "tests rc=$?" >> gpurun_out/r2s_tests.log; tail -3 gpurun_out/r2s_tests.log
-for b in 8 16 32; do
-  VP_BENCH_E2E_BLOCKS=$b timeout 300 python bench.py --steps 20 --warmup 5 --no-extra --no-cpu-baseline > gpurun_out/r2s_bench_$b.json 2>/dev/null; echo "blocks $b rc=$?"
-done
-python - <<'PY'
-import json
-for p in (8,16,32):
-    l=json.loads(open('gpurun_out/r2s_bench_%s.json'%p).read().strip().splitlines()[-1])
-    print(p, "step %.4f"%l["ms_per_step"], "e2e %.3f floor %.3f"%(l["e2e"]["ms_per_step"], l["e2e"]["pcie_floor_ms"]), l["parity"]["ok"], l["e2e"]["gpu_launches_per_step"])
-PY
+nvidia-smi topo -m > gpurun_out/r2u_topo8.txt 2>&1
+free -g | head -2 > gpurun_out/r2u_mem.txt; nproc >> gpurun_out/r2u_mem.txt
+timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus 8 --steps 20 --warmup 5 > gpurun_out/r2u_bench8.json 2> gpurun_out/r2u_bench8.err; echo "bench8 rc=$?"
+grep -v "^chunkset.c\|^mem.c" gpurun_out/r2u_bench8.err | tail -15
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29514 bench.py --gpus 4 --steps 20 --warmup 5 > gpurun_out/r2u_bench4.json 2> gpurun_out/r2u_bench4.err; echo "bench4 rc=$?"

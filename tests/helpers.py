@@ -155,6 +155,41 @@ class RefWorld:
                                       vp(hashes) if hashed else None, vp(counts))
         return t, hashes, counts
 
+    def run_engine_with_gfx(self, max_passes=600):
+        """Drive the reference's OWN dispatcher (chunkset_manage, chunkset.c:246-507) until every chunk's splat list is
+        published, handing each published chunk to the reference's gfx_update_svl (gfx/vsplat.c:197-338, compiled
+        unmodified against the GL capture shim) the way the game loop does.  Afterwards node_buffer() reads what the
+        reference would have left in GPU memory."""
+        import time
+        lib, n = self.lib, self.world.n_chunks
+        for i in range(n):                                    # request a splat rebuild of every chunk (game.c:621-624)
+            lib.vr_chunk_set_make_mesh(self.set, C.c_uint32(i), 1)
+            lib.vr_chunk_set_make_mesh(self.set, C.c_uint32(i), 0)
+        idle = 0
+        for _ in range(max_passes):
+            lib.vr_manage(self.set)
+            new = 0
+            for i in range(n):
+                if lib.vr_chunk_svl_dirty(self.set, C.c_uint32(i)):
+                    lib.vr_gfx_update_svl(self.set, C.c_uint32(i))
+                    new += 1
+            pending = sum(lib.vr_chunk_pending(self.set, C.c_uint32(i)) for i in range(n))
+            idle = idle + 1 if (new == 0 and pending == 0) else 0
+            if idle >= 2:
+                return
+            time.sleep(0.03)
+        raise AssertionError("the reference dispatcher did not drain")
+
+    def node_buffer(self, lod, node):
+        """(int16 items, bytes) of the level-`lod` node buffer gfx_update_svl built (GeometrySVL.vbo_items + buffer data)."""
+        data, size = C.c_void_p(), C.c_uint64()
+        self.lib.vr_gsvl_node.restype = C.c_uint32
+        items = self.lib.vr_gsvl_node(self.set, C.c_int(lod), C.c_uint32(node), C.byref(data), C.byref(size))
+        if not items:
+            return 0, np.zeros(0, np.int16)
+        assert size.value == items * 2
+        return items, np.frombuffer(C.string_at(data, size.value), np.int16)
+
     def edit_sphere(self, x, y, z, r, v):
         """chunkset_edit_sphere (edit.c:179-244) on the reference's own ChunkSet."""
         self.lib.vr_edit_sphere(self.set, x, y, z, r, v)

@@ -10,6 +10,7 @@ pytestmark = pytest.mark.skipif(not helpers.ref_available(), reason="oracle/_ref
 
 CASES = [
     (2, (1, 0, 0), 0.3), (3, (1, 1, 1), 0.5), (4, (1, 1, 2), 0.1), (4, (2, 0, 1), 0.9), (5, (1, 1, 1), 0.4),
+    (6, (1, 0, 1), 0.25), (7, (1, 0, 0), 0.04),          # the chunk sizes BASELINE configs C2-C4 (64) and C5 (128) use
 ]
 
 
@@ -28,8 +29,9 @@ def test_random_worlds_splat_and_mesh(rb, bits, density):
         assert np.array_equal(xa, xb), cid
 
 
-def test_terrain_world_hashes():
-    w = worldgen.World(1234, 5, (2, 1, 2))
+@pytest.mark.parametrize("rb,bits", [(5, (2, 1, 2)), (6, (1, 1, 1)), (7, (1, 0, 1))])
+def test_terrain_world_hashes(rb, bits):
+    w = worldgen.World(1234, rb, bits)
     o, r = helpers.OracleWorld(w), helpers.RefWorld(w)
     ids = np.arange(w.n_chunks, dtype=np.uint32)
     for mode in (0, 1):

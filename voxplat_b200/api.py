@@ -100,6 +100,7 @@ def load_library():
         "vp_world_save": (C.c_int, [vp, C.c_char_p, C.POINTER(C.c_uint64)]),
         "vp_world_load": (C.c_int, [vp, C.c_char_p]),
         "vp_world_file_info": (C.c_int, [C.c_char_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32 * 3), C.POINTER(C.c_uint64)]),
+        "vp_raycast": (C.c_int, [vp, C.c_uint32, vp, vp, vp, vp, vp]),
         "vp_halo_plane_bytes": (C.c_uint64, [vp]),
         "vp_ctx_border_stream": (vp, [vp]),
         "vp_device_count": (C.c_int32, []),
@@ -374,6 +375,17 @@ class Context:
         n = C.c_uint32()
         self._ck(self.lib.vp_edit_sphere(self.h, x, y, z, radius, voxel, _ptr(ids), ids.size, C.byref(n)))
         return ids[:n.value].copy()
+
+    def raycast(self, origins, vectors, normals=None):
+        """chunkset_edit_raycast_until_solid for n rays: returns (voxels[n], coords[n,3], normals[n,3])."""
+        o = np.ascontiguousarray(origins, dtype=np.float32).reshape(-1, 3)
+        v = np.ascontiguousarray(vectors, dtype=np.float32).reshape(-1, 3)
+        n = len(o)
+        coords = np.zeros((n, 3), np.uint32)
+        nrm = np.zeros((n, 3), np.int8) if normals is None else np.ascontiguousarray(normals, dtype=np.int8).reshape(n, 3).copy()
+        vox = np.zeros(n, np.uint8)
+        self._ck(self.lib.vp_raycast(self.h, n, _ptr(o), _ptr(v), _ptr(coords), _ptr(nrm), _ptr(vox)))
+        return vox, coords, nrm
 
     def download_shadow_rows(self, z0, z1):
         shw = ((1 << self.max_bitw[0]) + (1 << self.max_bitw[1])) << self.root_bitw

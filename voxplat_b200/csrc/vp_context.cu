@@ -990,28 +990,70 @@ extern "C" int vp_encode_chunks_rle(vp_ctx *c, const uint32_t *ids, uint32_t n, 
 
 extern "C" int vp_rle_compress(vp_ctx *c, const uint8_t *data, uint32_t length, uint32_t *out_words, uint32_t cap_words, uint32_t *n_words)
 {
-	if (!c || !data || !n_words) return vp_fail(c, VP_ERR_ARG, "vp_rle_compress: null argument");
-	if (length == 0 || (length & 15) || length > 0xFFFFFFu)
-		return vp_fail(c, VP_ERR_ARG, "vp_rle_compress: length must be a multiple of 16 and <= 0xFFFFFF (chunk volumes up to 128^3)");
+	if (!c || !data || !n_words || length == 0) return vp_fail(c, VP_ERR_ARG, "vp_rle_compress: null argument or empty input");
 	VP_CUDA(c, cudaSetDevice(c->cfg.device));
-	if ((size_t)(length + 1) * 4 > c->cfg.rle_arena_bytes) return vp_fail(c, VP_ERR_ARENA_FULL, "vp_rle_compress: rle arena too small");
-	int rc = dio_reserve(c, (size_t)length + 64);
+	// rle.h:7 takes any length.  The kernel works on 16-byte groups and packs a run into 24 bits, so the input is padded to a
+	// multiple of 16 with copies of its last byte (they extend the last run; taken off again below) and encoded in segments
+	// of at most 0xFFFFF0 bytes (no run of a segment reaches 24 bits); the host then joins runs across segment borders and
+	// applies the reference's split rule: a run stops when its count reaches 0xFFFFFF (rle.c:62).
+	constexpr uint32_t kSeg = 0xFFFFF0u;
+	const uint64_t padded = ((uint64_t)length + 15u) & ~15ull;
+	const uint32_t pad = (uint32_t)(padded - length), nseg = (uint32_t)((padded + kSeg - 1) / kSeg);
+	if ((padded + 4ull * nseg) * 4 > c->cfg.rle_arena_bytes) return vp_fail(c, VP_ERR_ARENA_FULL, "vp_rle_compress: rle arena too small");
+	int rc = dio_reserve(c, (size_t)padded + 64 + (size_t)nseg * 16);
 	if (rc) return rc;
 	unsigned long long *d_off = reinterpret_cast<unsigned long long *>(c->d_io);
-	uint32_t *d_cnt = reinterpret_cast<uint32_t *>(c->d_io + 8);
-	uint8_t *d_src = c->d_io + 64;
+	uint32_t *d_cnt = reinterpret_cast<uint32_t *>(c->d_io + (size_t)nseg * 8);
+	uint8_t *d_src = c->d_io + (((size_t)nseg * 12 + 63) & ~(size_t)63);
 	c->h_arena_state[5].cursor = 0; c->h_arena_state[5].capacity = c->cfg.rle_arena_bytes; c->h_arena_state[5].overflow = 0; c->h_arena_state[5].pad = 0;
 	VP_CUDA(c, cudaMemcpyAsync(c->d_arena_state + 2, c->h_arena_state + 5, sizeof(VpArenaDev), cudaMemcpyHostToDevice, c->stream));
 	VP_CUDA(c, cudaMemcpyAsync(d_src, data, length, cudaMemcpyHostToDevice, c->stream));
-	VP_CUDA(c, vp_launch_rle_encode(d_src, nullptr, 1, length, reinterpret_cast<uint32_t *>(c->d_rle_arena), c->d_arena_state + 2, d_off, d_cnt, c->stream));
-	c->launches++;
-	uint32_t cnt = 0;
-	VP_CUDA(c, cudaMemcpyAsync(&cnt, d_cnt, 4, cudaMemcpyDeviceToHost, c->stream));
+	if (pad) VP_CUDA(c, cudaMemsetAsync(d_src + length, data[length - 1], pad, c->stream));
+	for (uint32_t k = 0; k < nseg; k++) {
+		const uint32_t seg_len = (uint32_t)std::min<uint64_t>(kSeg, padded - (uint64_t)k * kSeg);
+		VP_CUDA(c, vp_launch_rle_encode(d_src + (size_t)k * kSeg, nullptr, 1, seg_len, reinterpret_cast<uint32_t *>(c->d_rle_arena), c->d_arena_state + 2,
+		                                d_off + k, d_cnt + k, c->stream));
+		c->launches++;
+	}
+	std::vector<unsigned long long> off(nseg);
+	std::vector<uint32_t> cnt(nseg);
+	VP_CUDA(c, cudaMemcpyAsync(off.data(), d_off, (size_t)nseg * 8, cudaMemcpyDeviceToHost, c->stream));
+	VP_CUDA(c, cudaMemcpyAsync(cnt.data(), d_cnt, (size_t)nseg * 4, cudaMemcpyDeviceToHost, c->stream));
 	VP_CUDA(c, cudaStreamSynchronize(c->stream));
-	*n_words = cnt;
-	if (cnt > cap_words || !out_words) return vp_fail(c, VP_ERR_ARENA_FULL, "vp_rle_compress: output buffer too small");
-	VP_CUDA(c, cudaMemcpyAsync(out_words, c->d_rle_arena, (size_t)cnt * 4, cudaMemcpyDeviceToHost, c->stream));
+	uint64_t raw = 0;
+	for (uint32_t k = 0; k < nseg; k++) { if (off[k] == ~0ull) return vp_fail(c, VP_ERR_ARENA_FULL, "vp_rle_compress: rle arena too small"); raw += cnt[k]; }
+	if (nseg == 1 && pad == 0) {               // the common case (a chunk volume): the device stream is the answer
+		*n_words = cnt[0];
+		if (cnt[0] > cap_words || !out_words) return vp_fail(c, VP_ERR_ARENA_FULL, "vp_rle_compress: output buffer too small");
+		VP_CUDA(c, cudaMemcpyAsync(out_words, reinterpret_cast<uint32_t *>(c->d_rle_arena) + off[0], (size_t)cnt[0] * 4, cudaMemcpyDeviceToHost, c->stream));
+		VP_CUDA(c, cudaStreamSynchronize(c->stream));
+		return VP_OK;
+	}
+	std::vector<uint32_t> seg(raw), out;
+	uint64_t at = 0;
+	for (uint32_t k = 0; k < nseg; k++) {
+		VP_CUDA(c, cudaMemcpyAsync(seg.data() + at, reinterpret_cast<uint32_t *>(c->d_rle_arena) + off[k], (size_t)cnt[k] * 4, cudaMemcpyDeviceToHost, c->stream));
+		at += cnt[k];
+	}
 	VP_CUDA(c, cudaStreamSynchronize(c->stream));
+	uint64_t acc = 0; uint32_t val = 0;
+	auto flush = [&] {
+		while (acc > 0xFFFFFFull) { out.push_back(0xFFFFFFu | (val << 24)); acc -= 0xFFFFFFull; }
+		if (acc) out.push_back((uint32_t)acc | (val << 24));
+		acc = 0;
+	};
+	for (uint64_t i = 0; i < raw; i++) {
+		const uint32_t wd = seg[i];
+		if (!wd) continue;                                   // a segment's terminator
+		if (acc && (wd >> 24) == val) acc += wd & 0xFFFFFFu;
+		else { flush(); val = wd >> 24; acc = wd & 0xFFFFFFu; }
+	}
+	acc -= pad;                                              // the padding copies the last byte: it sits in the last run
+	flush();
+	out.push_back(0u);
+	*n_words = (uint32_t)out.size();
+	if (out.size() > cap_words || !out_words) return vp_fail(c, VP_ERR_ARENA_FULL, "vp_rle_compress: output buffer too small");
+	memcpy(out_words, out.data(), out.size() * 4);
 	return VP_OK;
 }
 
@@ -1023,18 +1065,23 @@ extern "C" int vp_rle_decompress(vp_ctx *c, const uint32_t *words, uint32_t n_wo
 	for (uint32_t i = 0; i + 1 < n_words; i++) total += words[i] & 0xFFFFFFu;        // output size (metadata only)
 	*n_bytes = (uint32_t)std::min<uint64_t>(total, 0xFFFFFFFFu);
 	if (total > cap_bytes) return vp_fail(c, VP_ERR_ARENA_FULL, "vp_rle_decompress: output buffer too small");
-	if (total == 0 || (total & 15)) return vp_fail(c, VP_ERR_ARG, "vp_rle_decompress: decoded length must be a non-zero multiple of 16");
-	if ((size_t)n_words * 4 > c->cfg.rle_arena_bytes) return vp_fail(c, VP_ERR_ARENA_FULL, "vp_rle_decompress: rle arena too small");
-	int rc = dio_reserve(c, (size_t)total + 64);
+	if (total == 0 || total > 0xFFFFFFF0ull) return vp_fail(c, VP_ERR_ARG, "vp_rle_decompress: decoded length must be 1 .. 2^32 - 16 bytes");
+	// the kernel writes 16-byte groups: a stream of any other length gets one run of padding in front of its terminator
+	const uint32_t pad = (uint32_t)((16u - (total & 15u)) & 15u);
+	const uint32_t dev_words = n_words + (pad ? 1u : 0u);
+	if ((size_t)dev_words * 4 > c->cfg.rle_arena_bytes) return vp_fail(c, VP_ERR_ARENA_FULL, "vp_rle_decompress: rle arena too small");
+	int rc = dio_reserve(c, (size_t)total + pad + 64);
 	if (rc) return rc;
-	unsigned long long h_off[2] = {0, n_words};
+	unsigned long long h_off[2] = {0, dev_words};
+	const uint32_t tail[2] = {pad, 0u};
 	unsigned long long *d_off = reinterpret_cast<unsigned long long *>(c->d_io);
 	uint32_t *d_status = reinterpret_cast<uint32_t *>(c->d_io + 16);
 	uint8_t *d_dst = c->d_io + 64;
-	VP_CUDA(c, cudaMemcpyAsync(c->d_rle_arena, words, (size_t)n_words * 4, cudaMemcpyHostToDevice, c->stream));
+	VP_CUDA(c, cudaMemcpyAsync(c->d_rle_arena, words, (size_t)(n_words - 1) * 4, cudaMemcpyHostToDevice, c->stream));
+	VP_CUDA(c, cudaMemcpyAsync(c->d_rle_arena + (size_t)(n_words - 1) * 4, pad ? tail : tail + 1, pad ? 8 : 4, cudaMemcpyHostToDevice, c->stream));
 	VP_CUDA(c, cudaMemcpyAsync(d_off, h_off, 16, cudaMemcpyHostToDevice, c->stream));
 	VP_CUDA(c, cudaMemsetAsync(d_status, 0, 4, c->stream));
-	VP_CUDA(c, vp_launch_rle_decode(reinterpret_cast<const uint32_t *>(c->d_rle_arena), d_off, nullptr, 1, d_dst, (uint32_t)total, d_status, c->stream));
+	VP_CUDA(c, vp_launch_rle_decode(reinterpret_cast<const uint32_t *>(c->d_rle_arena), d_off, nullptr, 1, d_dst, (uint32_t)(total + pad), d_status, c->stream));
 	c->launches++;
 	uint32_t status = 0;
 	VP_CUDA(c, cudaMemcpyAsync(&status, d_status, 4, cudaMemcpyDeviceToHost, c->stream));
@@ -1334,6 +1381,31 @@ extern "C" int vp_edit_sphere(vp_ctx *c, int32_t x, int32_t y, int32_t z, uint32
 	VP_CUDA(c, vp_launch_extract_xfaces(c->rb, c->vox_pool, c->xlo_pool, c->xhi_pool, c->d_tmp_slots, (uint32_t)slots.size(), c->stream));
 	c->launches += 2;
 	VP_CUDA(c, cudaStreamSynchronize(c->stream));                   // `slots` goes out of scope
+	return VP_OK;
+}
+
+extern "C" int vp_raycast(vp_ctx *c, uint32_t n, const float *origins, const float *vectors, uint32_t *coords, int8_t *normals, uint8_t *voxels)
+{
+	if (!c || (n && (!origins || !vectors || !coords || !normals || !voxels))) return vp_fail(c, VP_ERR_ARG, "vp_raycast: null argument");
+	if (!n) return VP_OK;
+	VP_CUDA(c, cudaSetDevice(c->cfg.device));
+	// device scratch: origins | vectors | coords (n x 12 bytes each), normals (n x 3), voxels (n)
+	const size_t f3 = (size_t)n * 12, total = 3 * f3 + (size_t)n * 4 + 64;
+	int rc = dio_reserve(c, total);
+	if (rc) return rc;
+	float *d_o = reinterpret_cast<float *>(c->d_io), *d_v = reinterpret_cast<float *>(c->d_io + f3);
+	uint32_t *d_c = reinterpret_cast<uint32_t *>(c->d_io + 2 * f3);
+	int8_t *d_n = reinterpret_cast<int8_t *>(c->d_io + 3 * f3);
+	uint8_t *d_x = reinterpret_cast<uint8_t *>(c->d_io + 3 * f3 + (size_t)n * 3);
+	VP_CUDA(c, cudaMemcpyAsync(d_o, origins, f3, cudaMemcpyHostToDevice, c->stream));
+	VP_CUDA(c, cudaMemcpyAsync(d_v, vectors, f3, cudaMemcpyHostToDevice, c->stream));
+	VP_CUDA(c, cudaMemcpyAsync(d_n, normals, (size_t)n * 3, cudaMemcpyHostToDevice, c->stream));
+	VP_CUDA(c, vp_launch_raycast(vp_world_dev(c), c->vox_pool, n, d_o, d_v, d_c, d_n, d_x, c->stream));
+	c->launches++;
+	VP_CUDA(c, cudaMemcpyAsync(coords, d_c, f3, cudaMemcpyDeviceToHost, c->stream));
+	VP_CUDA(c, cudaMemcpyAsync(normals, d_n, (size_t)n * 3, cudaMemcpyDeviceToHost, c->stream));
+	VP_CUDA(c, cudaMemcpyAsync(voxels, d_x, n, cudaMemcpyDeviceToHost, c->stream));
+	VP_CUDA(c, cudaStreamSynchronize(c->stream));
 	return VP_OK;
 }
 

@@ -133,6 +133,8 @@ cudaError_t vp_launch_rle_encode(const uint8_t *src_base, const int32_t *d_slots
                                  VpArenaDev *state, unsigned long long *d_offsets, uint32_t *d_counts, cudaStream_t s);
 cudaError_t vp_launch_lod_nodes(int lod, const int bits[3], uint32_t n_nodes, const VpResultDev *d_chunk_res, const uint8_t *d_splat_arena,
                                 uint8_t *d_node_arena, VpArenaDev *state, VpNodeDev *d_nodes, unsigned long long *d_chunk_dst, cudaStream_t s);
+cudaError_t vp_launch_raycast(const VpWorldDev &w, const uint8_t *vox_pool, uint32_t n, const float *origins, const float *vectors,
+                              uint32_t *coords, int8_t *normals, uint8_t *voxels, cudaStream_t s);
 cudaError_t vp_launch_edit_sphere(const VpWorldDev &w, uint8_t *vox_pool, uint16_t *shadow, int cx, int cy, int cz, int radius, int voxel,
                                   int own_z0, int own_z1, cudaStream_t s);
 
