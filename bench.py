@@ -363,6 +363,8 @@ def bind_to_gpu_numa_node(device_index):
 
 
 class Comm:
+    device = "cuda"              # where the few scalars that cross ranks live (tests/test_bench_dryrun.py drives the same code over gloo)
+
     def __init__(self, args):
         import torch
         self.torch = torch
@@ -387,7 +389,7 @@ class Comm:
         self.torch.cuda.synchronize()
 
     def reduce(self, values, op="sum"):
-        t = self.torch.tensor(values, dtype=self.torch.float64, device="cuda")
+        t = self.torch.tensor(values, dtype=self.torch.float64, device=self.device)
         if self.dist:
             self.dist.all_reduce(t, op={"sum": self.dist.ReduceOp.SUM, "max": self.dist.ReduceOp.MAX, "min": self.dist.ReduceOp.MIN}[op])
         return [float(x) for x in t.tolist()]
@@ -396,9 +398,9 @@ class Comm:
 def pcie_floor_ms(comm, h2d_bytes, d2h_bytes, reps=3):
     """The copies of one e2e step alone (pinned memory, two streams), on all ranks at once: the floor of the e2e step."""
     torch = comm.torch
-    dev_out = torch.empty(max(d2h_bytes, 1), dtype=torch.uint8, device="cuda")
+    dev_out = torch.empty(max(d2h_bytes, 1), dtype=torch.uint8, device=comm.device)
     host_out = torch.empty(max(d2h_bytes, 1), dtype=torch.uint8).pin_memory()
-    dev_in = torch.empty(max(h2d_bytes, 1), dtype=torch.uint8, device="cuda")
+    dev_in = torch.empty(max(h2d_bytes, 1), dtype=torch.uint8, device=comm.device)
     host_in = torch.empty(max(h2d_bytes, 1), dtype=torch.uint8).pin_memory()
     s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
 
@@ -452,7 +454,7 @@ def run_world(args, comm, workload, steps, warmup, with_cpu=False, with_mesh_all
 
     out = None
     with torch.cuda.stream(stream):
-        rebuilder = slab.SlabRebuilder(ctx, rank, world_size, lambda n: torch.empty(n, dtype=torch.uint8, device="cuda"), dist=dist)
+        rebuilder = slab.SlabRebuilder(ctx, rank, world_size, lambda n: torch.empty(n, dtype=torch.uint8, device=comm.device), dist=dist)
         near = slab.near_camera_flags(own_ids, ROOT_BITW, bits)
         flags = np.where(near, vpb.VP_REBUILD_SPLAT | vpb.VP_REBUILD_MESH, vpb.VP_REBUILD_SPLAT).astype(np.uint8)
         ctx.batch_prepare(own_ids, per_chunk_flags=flags)
@@ -493,12 +495,15 @@ def run_world(args, comm, workload, steps, warmup, with_cpu=False, with_mesh_all
         comm.barrier()
         splat_iso_ms, _ = ctx.kernel_ms_history(iso_n)
         # ... and the mesh kernels of the near-field chunks alone
+        # (only the ranks near the camera have any; EVERY rank takes the barrier -- collectives never sit inside a
+        # rank-dependent branch in this file)
         mesh_iso_ms = [0.0]
         if near.any():
             ctx.batch_prepare(own_ids[near], flags=vpb.VP_REBUILD_MESH)
             for _ in range(iso_n):
                 ctx.rebuild_device()
-            comm.barrier()
+        comm.barrier()
+        if near.any():
             _, mesh_iso_ms = ctx.kernel_ms_history(iso_n)
         mesh_all = None
         if with_mesh_all:
@@ -562,15 +567,19 @@ def run_world(args, comm, workload, steps, warmup, with_cpu=False, with_mesh_all
         floor_ms = pcie_floor_ms(comm, h2d, d2h)
 
         # ---- parity guard: after every clock has stopped ----
-        chk_n, chk_border, chk_ok, chk_detail, chk_kind = parity_guard(
-            workload, bits, rank, world_size, z0, z1, own_ids, flags, (res, dev_splat, dev_mesh),
-            (nn_ids, r_e, np.asarray(sb_e), np.asarray(mb_e)))
+        try:
+            chk_n, chk_border, chk_ok, chk_detail, chk_kind = parity_guard(
+                workload, bits, rank, world_size, z0, z1, own_ids, flags, (res, dev_splat, dev_mesh),
+                (nn_ids, r_e, np.asarray(sb_e), np.asarray(mb_e)))
+        except Exception as exc:          # a checker problem on ONE rank must not leave the others waiting in a collective
+            chk_n, chk_border, chk_ok, chk_detail, chk_kind = 0, 0, None, "checker failed: %r" % (exc,), "none"
         if not chk_ok:
-            print("bench.py: PARITY MISMATCH on rank %d (%s): %s" % (rank, workload, chk_detail), file=sys.stderr, flush=True)
+            print("bench.py: %s on rank %d (%s): %s" % ("PARITY MISMATCH" if chk_ok is False else "parity unchecked", rank, workload, chk_detail),
+                  file=sys.stderr, flush=True)
 
     # ---- reduce the per-rank figures ----
     sb_a, mb_a, splats, faces = algorithmic_bytes(own_ids, solid, res, bits)
-    agg = comm.reduce([sb_a, mb_a, splats, faces, h2d, d2h, len(nn), chk_n, chk_border, 0 if chk_ok else 1])
+    agg = comm.reduce([sb_a, mb_a, splats, faces, h2d, d2h, len(nn), chk_n, chk_border, 1 if chk_ok is False else 0, 1 if chk_ok is None else 0])
     total_vox = float(nx * ny * nz) * N
     ms_per_step = total_ms / steps
     value = total_vox / (ms_per_step * 1e-3) / 1e9
@@ -620,7 +629,8 @@ def run_world(args, comm, workload, steps, warmup, with_cpu=False, with_mesh_all
                     "path": ("host RLE streams (pinned) -> vp_rebuild_from_rle (%d blocks pipelined: H2D + device decode | cull/LOD/splat/mesh | D2H) -> pinned host staging" % E2E_BLOCKS
                              if world_size == 1 else "host RLE streams (pinned) -> border rows: vp_upload_chunks_rle + NCCL plane exchange -> vp_rebuild_from_rle (8 blocks pipelined) -> pinned host staging"),
                     "gpu_launches_per_step": int(e2e_launches)},
-            "parity": {"chunks": int(agg[7]), "border_chunks": int(agg[8]), "ok": agg[9] == 0, "checker": chk_kind,
+            "parity": {"chunks": int(agg[7]), "border_chunks": int(agg[8]), "ok": (agg[9] == 0) if agg[10] == 0 else (False if agg[9] else None),
+                       "ranks_unchecked": int(agg[10]), "checker": chk_kind,
                        "what": "per rank: first, last (and one middle) chunk row; splat + mesh buffers of the timed device step and of the e2e call, FNV-1a 64 per chunk vs the checker on the same world"},
             "gpu_launches": int(launches),
             "clocks": clocks,
@@ -750,8 +760,8 @@ def run_c5(rb, bits, bursts=60):
     return out, bool(ok)
 
 
-def run_native(args):
-    comm = Comm(args)
+def run_native(args, comm=None):
+    comm = comm or Comm(args)
     n = comm.world_size
     ok_all = True
     line, ok = run_world(args, comm, args.workload, args.steps, args.warmup, with_cpu=(n == 1 and not args.no_cpu_baseline),
@@ -760,14 +770,23 @@ def run_native(args):
     extras = []
     if not args.no_extra and args.workload == "c2":
         if n == 1:
-            for fn in (run_c1, lambda: run_c5(5, (4, 2, 4)), lambda: run_c5(7, (3, 1, 3))):
-                r, ok = fn()
+            for name, fn in (("c1", run_c1), ("c5 chunk 32", lambda: run_c5(5, (4, 2, 4))), ("c5 chunk 128", lambda: run_c5(7, (3, 1, 3)))):
+                try:
+                    r, ok = fn()
+                except Exception as exc:
+                    print("bench.py: extra workload %s failed: %r" % (name, exc), file=sys.stderr, flush=True)
+                    r, ok = {"config": name, "error": repr(exc)}, True
                 extras.append(r)
                 ok_all &= ok
         else:
             todo = ["c3"] + (["c4"] if n == 8 else [])
             for wl in todo:
-                r, ok = run_world(args, comm, wl, max(3, min(args.steps, 10)), 3)
+                try:
+                    r, ok = run_world(args, comm, wl, max(3, min(args.steps, 10)), 3)
+                except Exception as exc:      # (the same exception on every rank: sizes are symmetric) keep the headline line
+                    print("bench.py: extra workload %s failed on rank %d: %r" % (wl, comm.rank, exc), file=sys.stderr, flush=True)
+                    extras.append({"config": config_dict(wl, n), "error": repr(exc)})
+                    break
                 ok_all &= ok
                 if r is not None:
                     extras.append({k: r[k] for k in ("config", "value", "unit", "ms_per_step", "steps", "scaling", "workload_stats", "roofline", "e2e", "parity", "gpu_launches")})

@@ -17,6 +17,7 @@
  * chunk id = (cz<<by | cy)<<bx | cx (chunkset.c:124-126); voxel index = (z<<rb | y)<<rb | x
  * (chunkset.c:128-130).  chunks[id]==NULL means "all air" (the reference's null chunk).
  */
+#include <math.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
@@ -349,3 +350,38 @@ VO_EXPORT uint32_t vo_lod_node(const int32_t bits[3], int32_t lod, uint32_t node
 	}
 	return total;
 }
+
+/* ---- pick ray: chunkset_edit_raycast_until_solid (chunkset/edit.c:248-314) ----
+ * The walk restated with every float operation spelled out -- IEEE divide, the sum of squares as one multiply and two
+ * fused multiply-adds in the association the reference build uses (fmaf(t2, t2, fmaf(t0, t0, t1 * t1))), float square
+ * root, unsigned <-> float conversions that stick at 0xFFFFFFFF for negative / too large values -- so that it takes the
+ * same side at every step as the compiled reference; this is the arithmetic the device kernel (vp_edit.cu k_raycast)
+ * uses, operation for operation.  `normal` is in/out like the reference's argument.  Returns the voxel hit (0 = none). */
+static uint32_t f2u_sat(float f) { return (!(f > -1.0f) || f >= 4294967296.0f) ? 0xFFFFFFFFu : (uint32_t)f; }
+
+#pragma GCC push_options
+#pragma GCC optimize ("fp-contract=off")
+VO_EXPORT int vo_raycast(const vo_world *w, const float origin[3], const float vector[3], uint32_t coord[3], int8_t normal[3])
+{
+	float d[3], next[3], step[3];
+	for (int i = 0; i < 3; i++) coord[i] = (uint32_t)(int)origin[i];
+	for (int i = 0; i < 3; i++) {
+		const float t0 = vector[0] / vector[i], t1 = vector[1] / vector[i], t2 = vector[2] / vector[i];
+		const float sq = t1 * t1;
+		d[i] = sqrtf(fmaf(t2, t2, fmaf(t0, t0, sq)));
+		if (0.0f > vector[i]) { step[i] = -1.0f; const float a = origin[i] - (float)coord[i]; next[i] = a * d[i]; }
+		else { step[i] = 1.0f; const float a = (float)coord[i] + 1.0f; const float b = a - origin[i]; next[i] = b * d[i]; }
+	}
+	for (int loops = 4095; loops > 0; loops--) {
+		int side = 0;
+		if (next[0] > next[1]) side = 1;
+		if (next[side] > next[2]) side = 2;
+		next[side] = next[side] + d[side];
+		coord[side] = f2u_sat((float)coord[side] + step[side]);
+		if (coord[0] >= wdim(w, 0) || coord[1] >= wdim(w, 1) || coord[2] >= wdim(w, 2)) continue;      /* edit.c:22-25 */
+		const uint8_t v = vox_at(w, coord[0], coord[1], coord[2]);
+		if (v) { normal[side] = (-vector[side] > 0.0f) ? 1 : -1; return v; }
+	}
+	return 0;
+}
+#pragma GCC pop_options

@@ -83,6 +83,15 @@ class OracleWorld:
         assert nv.value == f * 16 and ni.value == f * 6
         return vbo[:nv.value].copy(), ibo[:ni.value].copy()
 
+    def raycast(self, origin, vector, normal=(0, 0, 0)):
+        """Restated pick ray (vo_raycast): returns (voxel, coord[3], normal[3])."""
+        o = (C.c_float * 3)(*[float(x) for x in origin])
+        v = (C.c_float * 3)(*[float(x) for x in vector])
+        c = (C.c_uint32 * 3)()
+        m = (C.c_int8 * 3)(*normal)
+        hit = self.lib.vo_raycast(C.byref(self.w), o, v, c, m)
+        return hit, list(c), list(m)
+
     def rebuild(self, ids, mode, nthreads=0, hashed=True):
         """hashed=False: a timing run (no FNV pass over the outputs inside the clock); the hashes come back zero."""
         ids = np.ascontiguousarray(ids, dtype=np.uint32)
@@ -189,6 +198,15 @@ class RefWorld:
             return 0, np.zeros(0, np.int16)
         assert size.value == items * 2
         return items, np.frombuffer(C.string_at(data, size.value), np.int16)
+
+    def raycast(self, origin, vector, normal=(0, 0, 0)):
+        """chunkset_edit_raycast_until_solid (edit.c:248-314) as is: returns (voxel, coord[3], normal[3])."""
+        o = (C.c_float * 3)(*[float(x) for x in origin])
+        v = (C.c_float * 3)(*[float(x) for x in vector])
+        c = (C.c_uint32 * 3)()
+        m = (C.c_int8 * 3)(*normal)
+        hit = self.lib.vr_raycast(self.set, o, v, c, m)
+        return hit, list(c), list(m)
 
     def edit_sphere(self, x, y, z, r, v):
         """chunkset_edit_sphere (edit.c:179-244) on the reference's own ChunkSet."""

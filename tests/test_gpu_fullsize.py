@@ -62,30 +62,3 @@ def test_c2_world_byte_exact_hashes_and_properties():
         assert np.array_equal(res2["svl_items"], res["svl_items"])           # idempotent on identical input
     finally:
         ctx.close()
-
-
-@pytest.mark.skipif(not helpers.ref_available(), reason="oracle/_ref/libvoxref.so not built")
-@pytest.mark.parametrize("rb,bits,kind", [(7, (1, 0, 1), "terrain"), (7, (1, 0, 0), "random"), (6, (1, 1, 1), "random")])
-def test_large_chunks_against_the_compiled_reference(rb, bits, kind):
-    """Chunk 128 (BASELINE config C5) and 64 against the COMPILED reference itself, not only the restatement."""
-    w = worldgen.World(4321, rb, bits) if kind == "terrain" else helpers.random_world(4321 + rb, rb, bits, density=0.06, null_frac=0.0)
-    r = helpers.RefWorld(w)
-    ctx = vpb.Context(rb, bits, splat_arena_bytes=1 << 30, mesh_arena_bytes=2 << 30)
-    try:
-        nn = w.nonnull_ids()
-        ctx.upload_chunks_dense(nn, np.ascontiguousarray(w.dense[nn]))
-        ctx.upload_shadow_rows(0, w.shadow[:w.shw * w.dims[2]])
-        ids = np.arange(w.n_chunks, dtype=np.uint32)
-        res, splat, mesh = ctx.rebuild_batch(ids, vpb.VP_REBUILD_SPLAT | vpb.VP_REBUILD_MESH)
-        for k in range(w.n_chunks):
-            g, it = r.splat(k)
-            off = int(res["svl_offset"][k])
-            assert np.array_equal(res["svl_items"][k], it), k
-            assert np.array_equal(splat[off:off + g.size * 2].view(np.int16), g), k
-            v, x = r.mesh(k)
-            vo, io = int(res["vbo_offset"][k]), int(res["ibo_offset"][k])
-            assert res["vbo_items"][k] == v.size and res["ibo_items"][k] == x.size, k
-            assert np.array_equal(mesh[vo:vo + v.size * 2].view(np.int16), v), k
-            assert np.array_equal(mesh[io:io + x.size * 4].view(np.uint32), x), k
-    finally:
-        ctx.close()

@@ -43,28 +43,3 @@ def test_lod_nodes_match_oracle(rb, bits):
             assert int(nodes["items"].sum()) == int(items[:, lod].sum())
     finally:
         ctx.close()
-
-
-@pytest.mark.skipif(not helpers.ref_available(), reason="oracle/_ref/libvoxref.so not built")
-@pytest.mark.parametrize("rb,bits", [(4, (2, 1, 3)), (5, (2, 1, 2))])
-def test_lod_nodes_match_the_reference_gfx_update_svl(rb, bits):
-    """The device gather against the COMPILED reference: its dispatcher publishes every chunk, its gfx_update_svl
-    (gfx/vsplat.c:197-338, GL calls captured by oracle/gfx_shim) builds the node buffers."""
-    w = worldgen.World(2718, rb, bits)
-    r = helpers.RefWorld(w)
-    r.run_engine_with_gfx()
-    ctx = vpb.Context(rb, bits)
-    try:
-        upload_world(ctx, w)
-        ctx.rebuild_batch(np.arange(w.n_chunks, dtype=np.uint32), vpb.VP_REBUILD_SPLAT)
-        for lod in range(5):
-            nodes, buf, ms = ctx.build_lod_nodes(lod)
-            assert len(nodes) == 1 << sum(b - min(lod, b) for b in bits)
-            for node in range(len(nodes)):
-                want_n, want = r.node_buffer(lod, node)
-                assert nodes["items"][node] == want_n, (lod, node)
-                if want_n:
-                    off = int(nodes["offset"][node])
-                    assert np.array_equal(buf[off:off + want_n * 2].view(np.int16), want), (lod, node)
-    finally:
-        ctx.close()

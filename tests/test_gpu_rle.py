@@ -79,34 +79,3 @@ def test_flat_codec_edge_cases():
             ctx.upload_chunks_rle(np.array([0], np.uint32), np.array([5 | (3 << 24), 0], np.uint32), np.array([0, 2], np.uint64))
     finally:
         ctx.close()
-
-
-def test_flat_codec_any_length_and_run_split():
-    """rle.h:7 takes any length, and a run stops when its count reaches 0xFFFFFF (rle.c:62): lengths that are not a multiple
-    of 16, single bytes, and runs longer than 24 bits -- against the oracle encoder and, where the reference's scratch
-    allows it (SURVEY 8a' u4), the compiled reference itself."""
-    import ctypes as C
-    ctx = vpb.Context(5, (0, 0, 0), rle_arena_bytes=1 << 30)
-    try:
-        rng = np.random.default_rng(8)
-        cases = [np.array([9], np.uint8), np.array([0, 0, 0, 5, 5], np.uint8), np.full(17, 3, np.uint8),
-                 np.repeat(rng.integers(0, 256, 123).astype(np.uint8), 7)[:851],
-                 np.concatenate([np.zeros(1001, np.uint8), np.full(31, 4, np.uint8)])]
-        big = np.zeros(0x2000005, np.uint8)                       # 33.5 M bytes: two full 0xFFFFFF runs of zeros, then a remainder ...
-        big[0x1FFFFFF + 100:0x1FFFFFF + 200] = 77                 # ... interrupted by another value
-        big[-3:] = 5
-        cases.append(big)
-        cases.append(np.full(0xFFFFFF * 2, 1, np.uint8))          # exactly two maximal runs, no remainder word
-        for d in cases:
-            enc = ctx.rle_compress(d)
-            want = helpers.rle_encode(d)
-            assert np.array_equal(enc, want), d.size
-            assert (enc[:-1] & 0xFFFFFF).max() <= 0xFFFFFF and enc[-1] == 0
-            assert np.array_equal(ctx.rle_decompress(want, d.size), d), d.size
-            if helpers.ref_available() and want.size <= d.size // 4:
-                lib = helpers.ref_lib()
-                out = np.zeros(want.size + 8, np.uint32)
-                k = lib.vr_rle_compress(helpers.vp(d), C.c_uint32(d.size), helpers.vp(out), C.c_uint32(out.size))
-                assert k == enc.size and np.array_equal(out[:k], enc), d.size
-    finally:
-        ctx.close()
