@@ -1,6 +1,8 @@
+#!/bin/bash
+# Scratch script for `gpurun -- 'bash scripts/_run.sh'` calls.  RULE (learned the hard way in round 2):
+# every multi-GPU command gets its OWN tight timeout -- the box is charged N x wall time, and a deadlocked NCCL job
+# otherwise sits in the watchdog for ten minutes per launch.
+N=${1:-2}
 mkdir -p gpurun_out
-nvidia-smi topo -m > gpurun_out/r2u_topo8.txt 2>&1
-free -g | head -2 > gpurun_out/r2u_mem.txt; nproc >> gpurun_out/r2u_mem.txt
-timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus 8 --steps 20 --warmup 5 > gpurun_out/r2u_bench8.json 2> gpurun_out/r2u_bench8.err; echo "bench8 rc=$?"
-grep -v "^chunkset.c\|^mem.c" gpurun_out/r2u_bench8.err | tail -15
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29514 bench.py --gpus 4 --steps 20 --warmup 5 > gpurun_out/r2u_bench4.json 2> gpurun_out/r2u_bench4.err; echo "bench4 rc=$?"
+timeout 180 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29513 \
+  bench.py --gpus $N --steps 20 --warmup 5 > gpurun_out/bench$N.json 2> gpurun_out/bench$N.err; echo "bench$N rc=$?"
