@@ -91,10 +91,13 @@ def test_flat_codec_any_length_and_run_split():
         cases = [np.array([9], np.uint8), np.array([0, 0, 0, 5, 5], np.uint8), np.full(17, 3, np.uint8),
                  np.repeat(rng.integers(0, 256, 123).astype(np.uint8), 7)[:851],
                  np.concatenate([np.zeros(1001, np.uint8), np.full(31, 4, np.uint8)])]
-        big = np.zeros(0x2000005, np.uint8)                       # 33.5 M bytes: two full 0xFFFFFF runs of zeros, then a remainder ...
-        big[0x1FFFFFF + 100:0x1FFFFFF + 200] = 77                 # ... interrupted by another value
-        big[-3:] = 5
+        big = np.zeros(0x2000005, np.uint8)                       # 33.5 M bytes: a run of zeros longer than 0xFFFFFF (split + remainder) ...
+        big[0xFFFFFF + 100:0xFFFFFF + 200] = 77                   # ... another value, a second long run of zeros ...
+        big[-3:] = 5                                              # ... and a tail that is not a multiple of 16
         cases.append(big)
+        big2 = np.zeros(0x2000005, np.uint8)                      # zeros for two full runs and a remainder, across both 0xFFFFF0-byte segments
+        big2[-3:] = 5
+        cases.append(big2)
         cases.append(np.full(0xFFFFFF * 2, 1, np.uint8))          # exactly two maximal runs, no remainder word
         for d in cases:
             enc = ctx.rle_compress(d)
