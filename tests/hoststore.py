@@ -225,5 +225,58 @@ class HostContext:
     def kernel_launches(self):
         return self.launches
 
+    # ---- the rest of the Context surface the GPU tests use (tests/test_unverified_gpu_tests_dryrun.py) ----
+    def download_chunks_dense(self, ids):
+        out = np.zeros((len(ids), self.N), np.uint8)
+        for k, cid in enumerate(ids):
+            if int(cid) in self.chunks:
+                out[k] = self.chunks[int(cid)]
+        return out
+
+    def rle_compress(self, data):
+        return helpers.rle_encode(data)
+
+    def rle_decompress(self, words, cap_bytes):
+        return helpers.rle_decode(words, cap_bytes)
+
+    def raycast(self, origins, vectors, normals=None):
+        o = np.ascontiguousarray(origins, dtype=np.float32).reshape(-1, 3)
+        v = np.ascontiguousarray(vectors, dtype=np.float32).reshape(-1, 3)
+        n = len(o)
+        ptrs = (C.c_void_p * self.n_chunks)(*[self.chunks[i].ctypes.data if i in self.chunks else None for i in range(self.n_chunks)])
+        w = helpers.VoWorld(self.rb, (C.c_int32 * 3)(*self.bits), C.cast(ptrs, C.c_void_p), self.shadow.ctypes.data)
+        vox, coords = np.zeros(n, np.uint8), np.zeros((n, 3), np.uint32)
+        nrm = np.zeros((n, 3), np.int8) if normals is None else np.array(normals, np.int8).reshape(n, 3)
+        lib = helpers.oracle_lib()
+        for i in range(n):
+            c, m = (C.c_uint32 * 3)(), (C.c_int8 * 3)(*[int(x) for x in nrm[i]])
+            vox[i] = lib.vo_raycast(C.byref(w), (C.c_float * 3)(*o[i].tolist()), (C.c_float * 3)(*v[i].tolist()), c, m)
+            coords[i], nrm[i] = list(c), list(m)
+        return vox, coords, nrm
+
+    def build_lod_nodes(self, lod, download=True):
+        """The gather of gfx_update_svl over the splat lists of the last rebuild (which must have covered every chunk, in id order)."""
+        res, splat, _ = self.last
+        assert len(res) == self.n_chunks
+        lib = helpers.oracle_lib()
+        lib.vo_lod_node.restype = C.c_uint32
+        lists = [np.ascontiguousarray(splat[int(res["svl_offset"][c]):int(res["svl_offset"][c]) + int(res["svl_items_total"][c]) * 2]) if res["svl_items_total"][c]
+                 else np.zeros(8, np.uint8) for c in range(self.n_chunks)]
+        ptrs = (C.c_void_p * self.n_chunks)(*[a.ctypes.data for a in lists])
+        items = np.ascontiguousarray(res["svl_items"], np.uint32)
+        cbits = (C.c_int32 * 3)(*self.bits)
+        nn = 1 << sum(b - min(lod, b) for b in self.bits)
+        nodes = np.zeros(nn, vapi.NODE_DTYPE)
+        bufs, off = [], 0
+        for node in range(nn):
+            n = lib.vo_lod_node(cbits, lod, node, ptrs, helpers.vp(items), None)
+            nodes["items"][node], nodes["offset"][node] = n, off
+            if n:
+                out = np.zeros(n, np.int16)
+                lib.vo_lod_node(cbits, lod, node, ptrs, helpers.vp(items), helpers.vp(out))
+                bufs.append(out.view(np.uint8))
+                off += n * 2
+        return nodes, (np.concatenate(bufs) if bufs else np.zeros(0, np.uint8)), 0.0
+
     def kernel_ms_history(self, n):
         return np.full(n, 0.4), np.full(n, 0.1)
