@@ -186,6 +186,10 @@ static void vp_residency_pass(struct ChunkSet *set)
 	}
 }
 
+/* Test seam (NULL in production): called between the residency pass and the selection pass -- the window in which an edit
+ * could be lost before the dirty flag was consumed ahead of the voxel read (tests/test_dropin_mock.py edits a chunk here). */
+void (*vp_chunkset_manage_between_passes)(struct ChunkSet *set) = NULL;
+
 void chunkset_manage(struct ChunkSet *set)
 {
 	if (G.set != set) vp_attach(set);
@@ -193,6 +197,7 @@ void chunkset_manage(struct ChunkSet *set)
 	/* ---- 1. residency: every chunk whose voxels changed since the last pass goes to the device first, so
 	 * that the halos the kernels read are current even for chunks that are throttled below ---- */
 	vp_residency_pass(set);
+	if (vp_chunkset_manage_between_passes) vp_chunkset_manage_between_passes(set);
 
 	/* ---- 2. selection with the reference's predicates (chunkset.c:284-316); the dirty flag of the reference is the
 	 * `pending` flag here (consumed in step 1) ---- */
