@@ -43,11 +43,16 @@ def make_set(lib, w, mesh_ids=()):
     return s
 
 
-def published(lib, s, i, ack):
+def published(lib, s, i, ack, read=True):
+    """What chunkset_manage published for chunk i (optionally acknowledged like gfx_update_svl / gfx_update_mesh do).
+    read=False only acknowledges: the buffers may be replaced by the dispatcher at any time, and the real consumer reads
+    them under ChunkMD.mutex_svl (gfx/vsplat.c:271) -- a test thread that runs BESIDE the dispatcher must not touch them."""
     svl, vbo, ibo = C.c_void_p(), C.c_void_p(), C.c_void_p()
     items = (C.c_uint32 * 5)()
     tot, nv, ni = C.c_uint32(), C.c_uint32(), C.c_uint32()
     fl = lib.vr_chunk_published(s, C.c_uint32(i), C.byref(svl), items, C.byref(tot), C.byref(vbo), C.byref(nv), C.byref(ibo), C.byref(ni), ack)
+    if not read:
+        return fl, None, None, None
     return fl, list(items), (C.string_at(svl, tot.value * 2) if svl.value and tot.value else b""), \
         (nv.value, ni.value, C.string_at(vbo, nv.value * 2) if vbo.value and nv.value else b"", C.string_at(ibo, ni.value * 4) if ibo.value and ni.value else b"")
 
@@ -93,14 +98,36 @@ def test_dropin_bookkeeping_matches_the_reference_dispatcher(lib):
         assert pa[k] == pb[k], k
 
 
-def check_published_equals_final_world(lib, s, w):
+def test_rle_only_chunks_are_uploaded_as_streams(lib):
+    """Every chunk compressed before the first pass (the state of a world that was just loaded: `voxels == NULL`, only
+    `rle`): the residency pass sends the streams themselves (vp_multi_upload_chunks_rle, decoded on the other side), null
+    chunks as null -- no host decode.  Published geometry must equal the reference dispatcher's."""
+    w = worldgen.World(5, 4, (2, 1, 2))
+    a, b = make_set(lib, w, [0, 3]), make_set(lib, w, [0, 3])
+    lib.vr_world_compress_all(a)
+    lib.vr_world_compress_all(b)
+    pa = drain(lib, a, w.n_chunks, lib.vr_manage_cpu)
+    pb = drain(lib, b, w.n_chunks, lib.vr_manage)
+    assert pa.keys() == pb.keys() and len(pa) >= w.n_chunks
+    for k in pa:
+        assert pa[k] == pb[k], k
+
+
+def check_published_equals_final_world(lib, s, w, ignore_shadow_bit=False):
+    """ignore_shadow_bit: the shadow bit of a splat comes from height-map entry x + y (shadow.h:45-63), which an edit in a
+    DIFFERENT chunk of the same z row can change without making this chunk dirty -- the engine itself leaves such splats
+    stale until the chunk is rebuilt for another reason.  Positions and colours must always be current."""
     for i in range(w.n_chunks):
         out = np.zeros((w.R + 1) ** 3 * 5, np.int16)
         items = (C.c_uint32 * 5)()
         n = lib.vr_chunk_splat(s, C.c_uint32(i), helpers.vp(out), C.c_uint32(out.size), items)
         fl, got_items, got_svl, _ = published(lib, s, i, 0)
         assert got_items == list(items), i
-        assert got_svl == out[:n].tobytes(), i
+        want, got = out[:n].copy(), np.frombuffer(got_svl, np.int16).copy()
+        if ignore_shadow_bit:
+            want[3::4] &= ~np.int16(64)
+            got[3::4] &= ~np.int16(64)
+        assert np.array_equal(got, want), i
 
 
 def test_edit_between_the_two_passes_is_not_lost(lib):
@@ -135,30 +162,33 @@ def test_edit_between_the_two_passes_is_not_lost(lib):
 
 
 def test_no_edit_is_lost_while_the_dispatcher_runs(lib):
-    w = worldgen.World(77, 4, (2, 1, 2))
+    # 32^3 chunks and a bounded number of two-valued edits: the reference's rle_compress overflows its scratch once a chunk
+    # has more than N/4 runs (SURVEY 8a' u4), which noisy edits of tiny chunks reach quickly
+    w = worldgen.World(77, 5, (2, 1, 2))
     s = make_set(lib, w)
     drain(lib, s, w.n_chunks, lib.vr_manage)
     X, Y, Z = w.dims
     stop = threading.Event()
     edits = [0]
 
-    def editor():                                              # the game thread: brush edits as fast as it can
+    def editor():                                              # the game thread: brush edits, 400 of them
         rng = np.random.default_rng(3)
-        while not stop.is_set():
+        while not stop.is_set() and edits[0] < 400:
             x, y, z = int(rng.integers(0, X)), int(rng.integers(2, Y)), int(rng.integers(0, Z))
-            lib.vr_edit_sphere(s, x, y, z, int(rng.integers(1, 5)), int(rng.choice([0, 63, 21])))
+            lib.vr_edit_sphere(s, x, y, z, int(rng.integers(1, 4)), int(rng.choice([0, 63])))
             edits[0] += 1
+            time.sleep(0.002)
 
     def consumer():                                            # the GL thread: acknowledges what was published
         while not stop.is_set():
             for i in range(w.n_chunks):
-                published(lib, s, i, 1)
+                published(lib, s, i, 1, read=False)
             time.sleep(0.001)
 
     threads = [threading.Thread(target=editor), threading.Thread(target=consumer)]
     for t in threads:
         t.start()
-    t_end = time.time() + 3.0
+    t_end = time.time() + 2.5
     passes = 0
     while time.time() < t_end:                                 # the mesher thread: the drop-in dispatcher, back to back
         lib.vr_manage(s)
@@ -166,8 +196,8 @@ def test_no_edit_is_lost_while_the_dispatcher_runs(lib):
     stop.set()
     for t in threads:
         t.join()
-    assert edits[0] > 50 and passes > 50
+    assert edits[0] > 50 and passes > 20
     time.sleep(0.12)
     drain(lib, s, w.n_chunks, lib.vr_manage)
     # every chunk's last published splat list is the list of the final world
-    check_published_equals_final_world(lib, s, w)
+    check_published_equals_final_world(lib, s, w, ignore_shadow_bit=True)
