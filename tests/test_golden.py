@@ -68,3 +68,57 @@ def test_known_answer_vectors():
     assert [v & 0xFFFF for v in c0["vbo"][:4]] == [2, 1, 1, 0xC505]
     d = np.array(kat["rle"]["data"], np.uint8)
     assert helpers.rle_encode(d).tolist() == kat["rle"]["words"] == [3, 0x05000002, 0x07000001, 9, 0x09000001, 0]
+
+
+# ---- fixtures of the rows next to the path (rays, LOD nodes, edits), generated from the compiled reference too ----
+def load_secondary(name):
+    z = np.load(os.path.join(GOLD, name + ".npz"))
+    w, _ = load_fixture(str(z["world"]))
+    return w, z
+
+
+@pytest.mark.parametrize("name", ["rays_terrain_r32", "rays_random_r16"])
+def test_restated_raycast_matches_golden(name):
+    w, z = load_secondary(name)
+    o = helpers.OracleWorld(w)
+    for i in range(len(z["voxels"])):
+        hit, coord, normal = o.raycast(z["origins"][i], z["vectors"][i])
+        assert (hit, coord, normal) == (int(z["voxels"][i]), z["coords"][i].tolist(), z["normals"][i].tolist()), i
+
+
+def test_restated_node_gather_matches_golden():
+    import ctypes as C
+    w, z = load_secondary("nodes_terrain_r16")
+    o = helpers.OracleWorld(w)
+    lib = helpers.oracle_lib()
+    lib.vo_lod_node.restype = C.c_uint32
+    svl, items = [], np.zeros((w.n_chunks, 5), np.uint32)
+    for c in range(w.n_chunks):
+        g, it = o.splat(c)
+        svl.append(np.ascontiguousarray(g if g.size else np.zeros(4, np.int16)))
+        items[c] = it
+    ptrs = (C.c_void_p * w.n_chunks)(*[a.ctypes.data for a in svl])
+    cbits = (C.c_int32 * 3)(*w.max_bitw)
+    at = 0
+    for lod, node, n in z["nodes"]:
+        got = np.zeros(max(int(n), 1), np.int16)
+        assert lib.vo_lod_node(cbits, int(lod), int(node), ptrs, helpers.vp(items), helpers.vp(got)) == n, (lod, node)
+        assert np.array_equal(got[:n], z["data"][at:at + n]), (lod, node)
+        at += int(n)
+    assert at == z["data"].size
+
+
+def test_host_stand_in_edits_match_golden():
+    """tests/hoststore.HostContext.edit_sphere (the stand-in the CPU dry runs use) against the reference's edit burst."""
+    import hoststore
+    w, z = load_secondary("edits_terrain_r32")
+    ctx = hoststore.HostContext(w.root_bitw, w.max_bitw)
+    nn = w.nonnull_ids()
+    ctx.upload_chunks_dense(nn, w.dense[nn])
+    ctx.upload_shadow_rows(0, w.shadow[:w.shw * w.dims[2]])
+    offs = z["dirty_offsets"]
+    for k, (x, y, zz, r, v) in enumerate(z["edits"].tolist()):
+        dirty = ctx.edit_sphere(x, y, zz, r, v)
+        assert sorted(dirty.tolist()) == z["dirty"][offs[k]:offs[k + 1]].tolist(), k
+    assert np.array_equal(ctx.download_chunks_dense(np.arange(w.n_chunks)), z["dense"])
+    assert np.array_equal(ctx.download_shadow_rows(0, w.dims[2]), z["shadow"])

@@ -41,3 +41,7 @@ def test_slab_edits(zz):
 
 def test_raycast(zz):
     zz.test_raycast_matches_compiled_reference(5, (2, 1, 2), "terrain")
+
+
+def test_golden_rays_nodes_edits(zz):
+    zz.test_device_rays_nodes_edits_match_golden()

@@ -209,3 +209,46 @@ def test_raycast_matches_compiled_reference(rb, bits, kind):
     for k, name in enumerate(("voxel", "coord", "normal")):
         bad = np.nonzero((got[k] != want[k]).reshape(n, -1).any(axis=1))[0]
         assert len(bad) == 0, (name, bad[:5], got[k][bad[:5]], want[k][bad[:5]])
+
+
+# ---- the same three rows against the committed golden fixtures (tests/golden/, generated from the compiled reference):
+# ---- these do not need oracle/_ref on the box
+def test_device_rays_nodes_edits_match_golden():
+    from test_golden import load_secondary
+    for name in ("rays_terrain_r32", "rays_random_r16"):
+        w, z = load_secondary(name)
+        ctx = vpb.Context(w.root_bitw, w.max_bitw)
+        try:
+            upload_world(ctx, w)
+            vox, coords, nrm = ctx.raycast(z["origins"], z["vectors"])
+        finally:
+            ctx.close()
+        assert np.array_equal(vox, z["voxels"]) and np.array_equal(coords, z["coords"]) and np.array_equal(nrm, z["normals"]), name
+    w, z = load_secondary("nodes_terrain_r16")
+    ctx = vpb.Context(w.root_bitw, w.max_bitw)
+    try:
+        upload_world(ctx, w)
+        ctx.rebuild_batch(np.arange(w.n_chunks, dtype=np.uint32), vpb.VP_REBUILD_SPLAT)
+        at, by_lod = 0, {}
+        for lod, node, n in z["nodes"]:
+            if int(lod) not in by_lod:
+                by_lod[int(lod)] = ctx.build_lod_nodes(int(lod))
+            nodes, buf, _ = by_lod[int(lod)]
+            assert nodes["items"][int(node)] == n, (lod, node)
+            off = int(nodes["offset"][int(node)])
+            assert np.array_equal(buf[off:off + int(n) * 2].view(np.int16), z["data"][at:at + n]), (lod, node)
+            at += int(n)
+    finally:
+        ctx.close()
+    w, z = load_secondary("edits_terrain_r32")
+    ctx = vpb.Context(w.root_bitw, w.max_bitw)
+    try:
+        upload_world(ctx, w)
+        offs = z["dirty_offsets"]
+        for k, (x, y, zz, r, v) in enumerate(z["edits"].tolist()):
+            dirty = ctx.edit_sphere(x, y, zz, r, v)
+            assert sorted(dirty.tolist()) == z["dirty"][offs[k]:offs[k + 1]].tolist(), k
+        assert np.array_equal(ctx.download_chunks_dense(np.arange(w.n_chunks, dtype=np.uint32)), z["dense"])
+        assert np.array_equal(ctx.download_shadow_rows(0, w.dims[2]), z["shadow"])
+    finally:
+        ctx.close()
