@@ -7,6 +7,9 @@ that `pytest -x -m gpu` runs every test that HAS been verified on hardware befor
   * vp_raycast against chunkset_edit_raycast_until_solid
   * the flat RLE codec at any length, with the reference's run split at 0xFFFFFF
   * vp_build_lod_nodes against the reference's own gfx_update_svl (compiled unmodified, GL calls captured)
+  * rays, node buffers and an edit burst against the committed golden fixtures (no oracle/_ref needed on the box)
+
+tests/test_unverified_gpu_tests_dryrun.py runs every one of these functions on CPU with the oracle-backed stand-in context.
 """
 import ctypes as C
 
