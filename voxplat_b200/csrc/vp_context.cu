@@ -1377,8 +1377,10 @@ extern "C" int vp_edit_sphere(vp_ctx *c, int32_t x, int32_t y, int32_t z, uint32
 	if ((rc = push_slot_table(c, own.data(), (uint32_t)own.size()))) return rc;
 	VpWorldDev w = vp_world_dev(c);
 	VP_CUDA(c, vp_launch_edit_sphere(w, c->vox_pool, c->d_shadow, x, y, z, r, voxel, c->cfg.slab_z0, c->cfg.slab_z1, c->stream));
-	VP_CUDA(c, cudaMemcpyAsync(c->d_tmp_slots, slots.data(), slots.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
-	VP_CUDA(c, vp_launch_extract_xfaces(c->rb, c->vox_pool, c->xlo_pool, c->xhi_pool, c->d_tmp_slots, (uint32_t)slots.size(), c->stream));
+	if (!slots.empty()) {                 // (a slab context may own none of the box's chunks: only its height-map rows change)
+		VP_CUDA(c, cudaMemcpyAsync(c->d_tmp_slots, slots.data(), slots.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+		VP_CUDA(c, vp_launch_extract_xfaces(c->rb, c->vox_pool, c->xlo_pool, c->xhi_pool, c->d_tmp_slots, (uint32_t)slots.size(), c->stream));
+	}
 	c->launches += 2;
 	VP_CUDA(c, cudaStreamSynchronize(c->stream));                   // `slots` goes out of scope
 	return VP_OK;
