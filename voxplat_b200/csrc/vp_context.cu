@@ -1380,8 +1380,9 @@ extern "C" int vp_edit_sphere(vp_ctx *c, int32_t x, int32_t y, int32_t z, uint32
 	if (!slots.empty()) {                 // (a slab context may own none of the box's chunks: only its height-map rows change)
 		VP_CUDA(c, cudaMemcpyAsync(c->d_tmp_slots, slots.data(), slots.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
 		VP_CUDA(c, vp_launch_extract_xfaces(c->rb, c->vox_pool, c->xlo_pool, c->xhi_pool, c->d_tmp_slots, (uint32_t)slots.size(), c->stream));
+		c->launches++;
 	}
-	c->launches += 2;
+	c->launches++;
 	VP_CUDA(c, cudaStreamSynchronize(c->stream));                   // `slots` goes out of scope
 	return VP_OK;
 }
